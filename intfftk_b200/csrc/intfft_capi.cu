@@ -1,0 +1,339 @@
+// C-ABI of libintfft_b200 (include/intfft.h): plan = elaborated int_fftNk / int_ifftNk entity,
+// exec = a batch of frames clocked through it.  Host logic only; kernels live in intfft_tile.cu,
+// intfft_fast16.cu and intfft_util.cu.  There is no CPU compute path in this file.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "intfft_internal.h"
+
+using namespace intfft;
+
+struct intfft_plan : public Plan {};
+
+namespace {
+
+int scalar_bytes(int width) { return width <= 16 ? 2 : (width <= 32 ? 4 : 8); }
+
+// "does it elaborate" — see the citations on intfft_validate in include/intfft.h
+int validate(const intfft_generics *g)
+{
+    if (!g) return INTFFT_EINVAL;
+    if (g->nfft_log2 < 3 || g->nfft_log2 > 20) return INTFFT_EINVAL;
+    if ((g->format | 1) != 1 || (g->rndmode | 1) != 1 || (g->xser | 1) != 1 || (g->use_fly | 1) != 1 ||
+        (g->direction | 1) != 1)
+        return INTFFT_EINVAL;
+    if (g->twdl_width < 8 || g->twdl_width > (g->xser ? 27 : 25)) return INTFFT_EINVAL;
+    if (g->data_width < 8) return INTFFT_EINVAL;
+    // int_dif2_fly.vhd:331-338: RNDMODE = 1 with SCALE = 0 generates two drivers for wz_re / wz_im
+    if (g->direction == 0 && g->format == 1 && g->rndmode == 1) return INTFFT_EINVAL;
+    const CmultConsts cm = cmult_consts(g->twdl_width, g->xser);
+    const int n = g->nfft_log2;
+    for (int ii = 0; ii < n; ++ii) {
+        const int s = g->direction ? ii : n - 1 - ii;
+        const int dtw = g->data_width + ii * g->format;
+        const int dtwc = g->direction ? dtw : dtw + g->format;
+        if (s > 1 && dtwc >= cm.lim_none) return INTFFT_EINVAL;   // no multiplier is generated
+        if (dtw + 1 > 96) return INTFFT_EINVAL;                  // int_addsub_dsp48.vhd:16-22
+    }
+    const int worst = g->data_width + g->format * n + ((!g->format && g->rndmode) ? 1 : 0);
+    if (worst > 64) return INTFFT_EUNSUPPORTED;
+    return INTFFT_OK;
+}
+
+// split `g` stage bits starting at local bit `c` into rounds of <= 4, short round at the bottom;
+// DIF walks the bits downwards, DIT upwards
+void make_rounds(PassParams &kp, bool dit)
+{
+    const int full = kp.g / 4, rem = kp.g % 4;
+    int lo[8], cnt[8], nr = 0;
+    int bit = kp.c;
+    if (rem) { lo[nr] = bit; cnt[nr] = rem; ++nr; bit += rem; }
+    for (int i = 0; i < full; ++i) { lo[nr] = bit; cnt[nr] = 4; ++nr; bit += 4; }
+    kp.nrounds = nr;
+    for (int i = 0; i < nr; ++i) {
+        const int src = dit ? i : nr - 1 - i;
+        kp.r_lo[i] = (signed char)lo[src];
+        kp.r_n[i] = (signed char)cnt[src];
+    }
+}
+
+int pick_lane(int max_width, int max_dtwc, int tw)
+{
+    if (max_width <= 32) return LANE_I32_P64;
+    return (max_dtwc + tw <= 64) ? LANE_I64_P64 : LANE_I64_P128;
+}
+
+void build_passes(Plan &pl)
+{
+    const intfft_generics &g = pl.g;
+    const int n = g.nfft_log2;
+    const bool dit = g.direction != 0;
+    const int rnd_extra = (pl.mode == MODE_ROUND) ? 1 : 0;
+    const CmultConsts cm = cmult_consts(g.twdl_width, g.xser);
+
+    struct Span { int lo_bit, bits; bool strided; };
+    std::vector<Span> spans;
+    if (n <= 13) {
+        spans.push_back({0, n, false});
+    } else {
+        const int g_hi = (n - 12) < 4 ? 4 : (n - 12);
+        const int g_lo = n - g_hi;
+        if (!dit) { spans.push_back({g_lo, g_hi, true}); spans.push_back({0, g_lo, false}); }
+        else      { spans.push_back({0, g_lo, false}); spans.push_back({g_lo, g_hi, true}); }
+    }
+
+    int stages_done = 0;
+    for (size_t i = 0; i < spans.size(); ++i) {
+        const Span &sp = spans[i];
+        PassDesc pd{};
+        PassParams &kp = pd.kp;
+        kp.n = n;
+        kp.L = (!sp.strided && n == 13) ? 13 : 12;
+        kp.g = sp.bits;
+        kp.pb = sp.lo_bit;
+        kp.c = sp.strided ? kp.L - sp.bits : 0;
+        kp.dw = g.data_width;
+        kp.format = g.format;
+        kp.cm = cm;
+        kp.total = pl.batch << n;
+        kp.n_tiles = sp.strided ? (pl.batch << (n - kp.L)) : ((kp.total + (1ll << kp.L) - 1) >> kp.L);
+        make_rounds(kp, dit);
+        const int w_in = g.data_width + stages_done * g.format;
+        const int w_out = g.data_width + (stages_done + sp.bits) * g.format;
+        kp.in_sb = scalar_bytes(w_in);
+        kp.out_sb = scalar_bytes(w_out);
+        kp.in_wrap = (i == 0) ? 1 : 0;
+        // widest multiplier operand inside this pass: DIF multiplies the stage output, DIT its input
+        const int max_dtwc = dit ? (w_out - g.format) : w_out;
+        pd.lane = pick_lane(w_out + rnd_extra, max_dtwc, g.twdl_width);
+        pd.threads = 1 << (kp.L - 4);
+        pd.smem_bytes = ((size_t)1 << kp.L) * (pd.lane == LANE_I32_P64 ? 8 : 16);
+        pd.scratch_in = pd.scratch_out = -1;
+        pd.fast16 = false;
+        stages_done += sp.bits;
+        pl.passes.push_back(pd);
+    }
+    // wire intermediates: a pass writes straight into the user's output buffer when its container
+    // already has the final size (later passes then run in place), otherwise into plan scratch
+    for (size_t i = 0; i + 1 < pl.passes.size(); ++i) {
+        PassDesc &a = pl.passes[i], &b = pl.passes[i + 1];
+        if (a.kp.out_sb != pl.out_sb) {
+            a.scratch_out = 0;
+            b.scratch_in = 0;
+            const size_t need = (size_t)a.kp.total * 2 * a.kp.out_sb;
+            if (need > pl.scratch_bytes[0]) pl.scratch_bytes[0] = need;
+        }
+    }
+    if (pl.passes.size() == 1 && g.use_fly && fast16_supported(g) && !std::getenv("INTFFT_DISABLE_FAST16"))
+        pl.passes[0].fast16 = true;
+}
+
+int upload_twiddles(Plan &pl)
+{
+    const int n = pl.g.nfft_log2;
+    const size_t cnt = (size_t)1 << n;
+    std::vector<int2> tab(cnt, make_int2(0, 0));
+    std::vector<int32_t> re(cnt / 2), im(cnt / 2);
+    for (int s = 2; s < n; ++s) {
+        twiddle_stage_table(s, pl.g.twdl_width, pl.g.xser, re.data(), im.data());
+        for (size_t k = 0; k < ((size_t)1 << s); ++k) tab[((size_t)1 << s) + k] = make_int2(re[k], im[k]);
+    }
+    if (cudaMalloc(&pl.d_tw, cnt * sizeof(int2)) != cudaSuccess) return INTFFT_ENOMEM;
+    if (cudaMemcpy(pl.d_tw, tab.data(), cnt * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) return INTFFT_ECUDA;
+    if (pl.g.twdl_width <= 16) {
+        std::vector<uint32_t> t16(cnt);
+        for (size_t i = 0; i < cnt; ++i)
+            t16[i] = ((uint32_t)(uint16_t)tab[i].x) | ((uint32_t)(uint16_t)tab[i].y << 16);
+        if (cudaMalloc(&pl.d_tw16, cnt * sizeof(uint32_t)) != cudaSuccess) return INTFFT_ENOMEM;
+        if (cudaMemcpy(pl.d_tw16, t16.data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) return INTFFT_ECUDA;
+    }
+    return INTFFT_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (ok && prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int intfft_validate(const intfft_generics *g) { return validate(g); }
+
+int intfft_plan_create(intfft_plan **out, const intfft_generics *g, int64_t batch, int device)
+{
+    if (!out) return INTFFT_EINVAL;
+    *out = nullptr;
+    int st = validate(g);
+    if (st) return st;
+    if (batch < 1 || (batch << g->nfft_log2) > (1ll << 40)) return INTFFT_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return INTFFT_ECUDA;
+    DeviceGuard guard(device);
+    if (!guard.ok) return INTFFT_ECUDA;
+
+    intfft_plan *pl = new (std::nothrow) intfft_plan();
+    if (!pl) return INTFFT_ENOMEM;
+    pl->g = *g;
+    pl->batch = batch;
+    pl->device = device;
+    pl->mode = g->format ? MODE_UNSCALED : (g->rndmode ? MODE_ROUND : MODE_TRUNC);
+    pl->in_width = g->data_width;
+    pl->out_width = g->data_width + g->format * g->nfft_log2;
+    pl->in_sb = scalar_bytes(pl->in_width);
+    pl->out_sb = scalar_bytes(pl->out_width);
+    cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, device);
+    build_passes(*pl);
+    st = upload_twiddles(*pl);
+    if (st == INTFFT_OK && pl->scratch_bytes[0]) {
+        if (cudaMalloc(&pl->scratch[0], pl->scratch_bytes[0]) != cudaSuccess) st = INTFFT_ENOMEM;
+    }
+    if (st != INTFFT_OK) { intfft_plan_destroy(pl); return st; }
+    *out = pl;
+    return INTFFT_OK;
+}
+
+int intfft_plan_destroy(intfft_plan *p)
+{
+    if (!p) return INTFFT_EINVAL;
+    DeviceGuard guard(p->device);
+    cudaFree(p->d_tw);
+    cudaFree(p->d_tw16);
+    cudaFree(p->scratch[0]);
+    cudaFree(p->scratch[1]);
+    cudaFree(p->h2d);
+    cudaFree(p->d2h);
+    delete p;
+    return INTFFT_OK;
+}
+
+int intfft_query(const intfft_plan *p, intfft_layout *l)
+{
+    if (!p || !l) return INTFFT_EINVAL;
+    l->n = 1ll << p->g.nfft_log2;
+    l->batch = p->batch;
+    l->in_width = p->in_width;
+    l->out_width = p->out_width;
+    l->in_scalar_bytes = p->in_sb;
+    l->out_scalar_bytes = p->out_sb;
+    l->in_bytes = p->batch * l->n * 2 * p->in_sb;
+    l->out_bytes = p->batch * l->n * 2 * p->out_sb;
+    l->n_passes = p->g.use_fly ? (int32_t)p->passes.size() : 1;
+    int lane = 32;
+    for (const PassDesc &pd : p->passes) if (pd.lane != LANE_I32_P64) lane = 64;
+    l->lane_bits = lane;
+    return INTFFT_OK;
+}
+
+int intfft_exec(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream)
+{
+    if (!p || !d_in || !d_out) return INTFFT_EINVAL;
+    if (d_in == d_out && p->in_sb != p->out_sb) return INTFFT_EINVAL;
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return INTFFT_ECUDA;
+    const long long n_scalars = (p->batch << p->g.nfft_log2) * 2;
+    if (!p->g.use_fly) {
+        const int e = launch_bypass(d_in, d_out, n_scalars, p->in_sb, p->out_sb, p->g.data_width,
+                                    p->g.format, cuda_stream);
+        return e ? INTFFT_ECUDA : INTFFT_OK;
+    }
+    const bool dit = p->g.direction != 0;
+    for (size_t i = 0; i < p->passes.size(); ++i) {
+        PassDesc &pd = p->passes[i];
+        pd.kp.in = (i == 0) ? d_in : (pd.scratch_in >= 0 ? p->scratch[pd.scratch_in] : d_out);
+        pd.kp.out = (i + 1 == p->passes.size()) ? d_out : (pd.scratch_out >= 0 ? p->scratch[pd.scratch_out] : d_out);
+        pd.kp.tw = p->d_tw;
+        const int e = pd.fast16 ? launch_fast16(pd, p->mode, dit, p->d_tw16, p->num_sms, cuda_stream)
+                                : launch_tile_pass(pd, p->mode, dit, p->num_sms, cuda_stream);
+        if (e) return INTFFT_ECUDA;
+    }
+    return INTFFT_OK;
+}
+
+int intfft_exec_host(intfft_plan *p, const void *h_in, void *h_out)
+{
+    if (!p || !h_in || !h_out) return INTFFT_EINVAL;
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return INTFFT_ECUDA;
+    intfft_layout l;
+    intfft_query(p, &l);
+    if (!p->h2d && cudaMalloc(&p->h2d, (size_t)l.in_bytes) != cudaSuccess) return INTFFT_ENOMEM;
+    if (!p->d2h && cudaMalloc(&p->d2h, (size_t)l.out_bytes) != cudaSuccess) return INTFFT_ENOMEM;
+    if (cudaMemcpyAsync(p->h2d, h_in, (size_t)l.in_bytes, cudaMemcpyHostToDevice, 0) != cudaSuccess) return INTFFT_ECUDA;
+    const int st = intfft_exec(p, p->h2d, p->d2h, nullptr);
+    if (st) return st;
+    if (cudaMemcpyAsync(h_out, p->d2h, (size_t)l.out_bytes, cudaMemcpyDeviceToHost, 0) != cudaSuccess) return INTFFT_ECUDA;
+    return cudaStreamSynchronize(0) == cudaSuccess ? INTFFT_OK : INTFFT_ECUDA;
+}
+
+int intfft_twiddles(const intfft_generics *g, int stage, int32_t *h_re, int32_t *h_im)
+{
+    if (!g || !h_re || !h_im || stage < 2 || stage > 19) return INTFFT_EINVAL;
+    if (g->twdl_width < 8 || g->twdl_width > ((g->xser & 1) ? 27 : 25)) return INTFFT_EINVAL;
+    twiddle_stage_table(stage, g->twdl_width, g->xser & 1, h_re, h_im);
+    return INTFFT_OK;
+}
+
+int intfft_bitrev(int nfft_log2, int scalar_bytes_, int64_t batch, const void *d_in, void *d_out,
+                  int device, void *cuda_stream)
+{
+    if (nfft_log2 < 1 || nfft_log2 > 30 || batch < 1 || !d_in || !d_out || d_in == d_out) return INTFFT_EINVAL;
+    if (scalar_bytes_ != 2 && scalar_bytes_ != 4 && scalar_bytes_ != 8) return INTFFT_EINVAL;
+    DeviceGuard guard(device);
+    if (!guard.ok) return INTFFT_ECUDA;
+    return launch_bitrev(nfft_log2, scalar_bytes_, batch, d_in, d_out, cuda_stream) ? INTFFT_ECUDA : INTFFT_OK;
+}
+
+int intfft_fill_random(void *d_buf, int64_t n_scalars, int sb, int width, uint64_t seed, int device, void *cuda_stream)
+{
+    if (!d_buf || n_scalars < 0 || (sb != 2 && sb != 4 && sb != 8) || width < 1 || width > 8 * sb) return INTFFT_EINVAL;
+    DeviceGuard guard(device);
+    if (!guard.ok) return INTFFT_ECUDA;
+    return launch_fill_random(d_buf, n_scalars, sb, width, seed, cuda_stream) ? INTFFT_ECUDA : INTFFT_OK;
+}
+
+int intfft_checksum(const void *d_buf, int64_t n_scalars, int sb, uint64_t *h_sum, int device, void *cuda_stream)
+{
+    if (!d_buf || !h_sum || n_scalars < 0 || (sb != 2 && sb != 4 && sb != 8)) return INTFFT_EINVAL;
+    DeviceGuard guard(device);
+    if (!guard.ok) return INTFFT_ECUDA;
+    uint64_t *d_sum = nullptr;
+    if (cudaMalloc(&d_sum, sizeof(uint64_t)) != cudaSuccess) return INTFFT_ENOMEM;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = INTFFT_OK;
+    if (cudaMemsetAsync(d_sum, 0, sizeof(uint64_t), st) != cudaSuccess) rc = INTFFT_ECUDA;
+    if (!rc && launch_checksum(d_buf, n_scalars, sb, d_sum, cuda_stream)) rc = INTFFT_ECUDA;
+    if (!rc && cudaMemcpyAsync(h_sum, d_sum, sizeof(uint64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = INTFFT_ECUDA;
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = INTFFT_ECUDA;
+    cudaFree(d_sum);
+    return rc;
+}
+
+int64_t intfft_launch_count(void) { return (int64_t)launches(); }
+
+const char *intfft_strerror(int status)
+{
+    switch (status) {
+    case INTFFT_OK: return "ok";
+    case INTFFT_EINVAL: return "invalid argument, or generics that do not elaborate in the reference";
+    case INTFFT_ECUDA: return "CUDA error (no usable device, or a launch / copy failed)";
+    case INTFFT_ENOMEM: return "out of memory";
+    case INTFFT_EUNSUPPORTED: return "legal in the reference but wider than this build's 64-bit lanes";
+    default: return "unknown status";
+    }
+}
+
+int intfft_version(void) { return 100; }
+
+}  // extern "C"

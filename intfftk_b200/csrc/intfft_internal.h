@@ -1,0 +1,89 @@
+// Internal declarations shared by the host-side plan code and the sm_100a kernels.
+// Nothing here crosses the C-ABI (include/intfft.h).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include <vector_types.h>
+
+#include "../../include/intfft.h"
+
+namespace intfft {
+
+// ---- complex-multiplier arrangement (int_cmult_dsp48.vhd:182-434), plan-wide constants --------
+// variant chosen per stage by the multiplier data width dtwc:
+//   dtwc < lim_single           -> one DSP48 pair:   (P2 +- P1) >> sh_single
+//   lim_single <= dtwc < lim_dbl-> double:           wrap48((P2>>k_pre) +- (P1>>k_pre)) >> sh_post
+//   lim_dbl <= dtwc             -> triple:           wrap((P2>>sh_single)) +- wrap((P1>>sh_single))
+struct CmultConsts {
+    int lim_single, lim_dbl, lim_none;
+    int sh_single, k_pre, sh_post;
+};
+CmultConsts cmult_consts(int twdl_width, int xser);
+
+// ---- twiddle generator: rom_twiddle_int.vhd + row_twiddle_tay.vhd, host side ------------------
+// fills re/im[0 .. 2^stage) with the stream rom_twiddle_int(STAGE = stage) produces.
+void twiddle_stage_table(int stage, int twdl_width, int xser, int32_t *re, int32_t *im);
+
+// ---- kernel-facing description of one pass over the data --------------------------------------
+enum LaneKind { LANE_I32_P64 = 0, LANE_I64_P64 = 1, LANE_I64_P128 = 2 };
+enum ModeKind { MODE_TRUNC = 0, MODE_ROUND = 1, MODE_UNSCALED = 2 };
+
+struct PassParams {
+    const void *in;
+    void *out;
+    const int2 *tw;        // twiddles, entry (1 << s) + k for stage s >= 2
+    long long total;       // batch * N complex samples
+    long long n_tiles;
+    int n;                 // NFFT
+    int L;                 // log2 samples per tile (threads = 2^(L-4))
+    int c;                 // log2 contiguous run ("column") length inside a tile
+    int pb;                // lowest global bit handled by this pass
+    int g;                 // number of stage bits handled by this pass (local bits [c, c+g))
+    int dw;                // DATA_WIDTH
+    int format;            // FORMAT
+    int in_sb, out_sb;     // scalar bytes of the containers this pass reads / writes
+    int in_wrap;           // wrap loaded scalars to dw bits (first pass only)
+    CmultConsts cm;
+    int nrounds;
+    signed char r_lo[8];   // local bit where round r starts
+    signed char r_n[8];    // stage bits in round r (1..4)
+};
+
+struct PassDesc {
+    PassParams kp;         // in/out/tw/n_tiles filled at exec time
+    int lane;              // LaneKind
+    int threads;
+    size_t smem_bytes;
+    int scratch_in, scratch_out;  // -1 = user buffer, else index of plan scratch buffer
+    bool fast16;           // handled by the specialised packed-16 kernel
+};
+
+struct Plan {
+    intfft_generics g;
+    int64_t batch;
+    int device;
+    int mode;              // ModeKind
+    int in_width, out_width, in_sb, out_sb;
+    std::vector<PassDesc> passes;
+    int2 *d_tw = nullptr;        // device twiddle table (int32 pairs)
+    uint32_t *d_tw16 = nullptr;  // device twiddle table, packed int16 pairs (TW <= 16 only)
+    void *scratch[2] = {nullptr, nullptr};
+    size_t scratch_bytes[2] = {0, 0};
+    void *h2d = nullptr, *d2h = nullptr;  // device staging for intfft_exec_host
+    int num_sms = 0;
+};
+
+// kernels (intfft_tile.cu / intfft_fast16.cu / intfft_util.cu); all return cudaError_t as int
+int launch_tile_pass(const PassDesc &pd, int mode, bool dit, int num_sms, void *stream);
+int launch_fast16(const PassDesc &pd, int mode, bool dit, const uint32_t *tw16, int num_sms, void *stream);
+bool fast16_supported(const intfft_generics &g);
+int launch_bypass(const void *in, void *out, long long n_scalars, int in_sb, int out_sb, int dw,
+                  int zero_extend, void *stream);
+int launch_bitrev(int nfft_log2, int scalar_bytes, long long batch, const void *in, void *out, void *stream);
+int launch_fill_random(void *buf, long long n_scalars, int sb, int width, uint64_t seed, void *stream);
+int launch_checksum(const void *buf, long long n_scalars, int sb, uint64_t *d_sum, void *stream);
+void count_launch(int n = 1);
+long long launches();
+
+}  // namespace intfft

@@ -1,0 +1,181 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle: bit-exact, same seeded inputs.
+
+Every test here needs a B200 (`-m gpu`).  Inputs are full-scale uniform (so two's-complement wrap in
+the multipliers is exercised, as in the reference) unless a test says otherwise."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked test running without a CUDA device")
+
+
+@pytest.fixture(scope="module")
+def ib():
+    _need_gpu()
+    import intfftk_b200
+    intfftk_b200.lib()          # raises if the CUDA library is missing: no fallback
+    return intfftk_b200
+
+
+def _run_both(ib, co, batch, seed=1, threads=0, via="host", **kw):
+    g = ib.Generics(**{k: v for k, v in kw.items() if k != "direction"})
+    direction = kw.get("direction", 0)
+    og = co.generics(g.NFFT, g.DATA_WIDTH, g.TWDL_WIDTH, g.FORMAT, g.RNDMODE, 1 if g.XSER == "NEW" else 0,
+                     g.USE_FLY, direction)
+    n = 1 << g.NFFT
+    x = co.fill_random(batch * n * 2, g.DATA_WIDTH, seed).reshape(batch, n, 2)
+    want = co.batch(og, x, threads)
+    core = ib.Core(g, batch, direction)
+    if via == "host":
+        got = core.exec_host(x)
+    else:
+        d_in = torch.from_numpy(x).cuda()
+        got = core.exec(d_in).cpu().numpy()
+    core.close()
+    return got, want
+
+
+SMALL = []
+for nfft in (3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13):
+    for direction in (0, 1):
+        for fmt, rnd in ((0, 0), (0, 1), (1, 0)):
+            SMALL.append((nfft, direction, fmt, rnd))
+
+
+@pytest.mark.parametrize("nfft,direction,fmt,rnd", SMALL)
+def test_parity_16bit_all_modes(ib, oracle, nfft, direction, fmt, rnd):
+    batch = max(3, 5000 >> nfft)
+    got, want = _run_both(ib, oracle, batch, seed=nfft * 8 + direction * 4 + fmt * 2 + rnd, NFFT=nfft, DATA_WIDTH=16,
+                          TWDL_WIDTH=16, FORMAT=fmt, RNDMODE=rnd, direction=direction)
+    assert got.dtype == want.dtype
+    assert np.array_equal(got, want)
+
+
+WIDTHS = [(8, 8, "NEW"), (12, 16, "OLD"), (18, 16, "NEW"), (18, 18, "NEW"), (24, 17, "OLD"), (25, 16, "OLD"),
+          (27, 16, "NEW"), (28, 16, "NEW"), (31, 12, "NEW"), (32, 16, "OLD"),
+          (16, 19, "NEW"), (18, 24, "NEW"), (19, 25, "OLD"), (30, 27, "NEW"),          # TW >= 19: single25 / dbl35
+          (36, 16, "NEW"), (40, 18, "NEW"), (44, 16, "OLD"), (45, 16, "NEW"), (50, 16, "NEW"),   # dbl18 / trpl18
+          (36, 22, "NEW"), (48, 19, "OLD"), (52, 27, "NEW"), (60, 16, "NEW"), (64, 10, "OLD")]
+
+
+@pytest.mark.parametrize("dw,tw,xser", WIDTHS)
+@pytest.mark.parametrize("direction", [0, 1])
+def test_parity_widths_and_multiplier_variants(ib, oracle, dw, tw, xser, direction):
+    for fmt, rnd in ((0, 0), (0, 1), (1, 0)):
+        nfft = 7
+        if tw >= 19 and dw + fmt * nfft + (1 - direction) * fmt > 52:
+            continue                                    # no trpl52 beyond 52 bits
+        if dw + fmt * nfft + (rnd if not fmt else 0) > 64:
+            continue                                    # beyond the 64-bit lanes
+        got, want = _run_both(ib, oracle, 9, seed=dw * 100 + tw, NFFT=nfft, DATA_WIDTH=dw, TWDL_WIDTH=tw,
+                              FORMAT=fmt, RNDMODE=rnd, XSER=xser, direction=direction)
+        assert np.array_equal(got, want), (fmt, rnd)
+
+
+@pytest.mark.parametrize("nfft,dw,fmt,direction", [(14, 16, 0, 0), (14, 16, 0, 1), (15, 18, 1, 0), (16, 24, 1, 0),
+                                                   (16, 16, 0, 1), (17, 16, 0, 0), (18, 12, 1, 1)])
+def test_parity_multipass(ib, oracle, nfft, dw, fmt, direction):
+    got, want = _run_both(ib, oracle, 3, seed=nfft, via="device", NFFT=nfft, DATA_WIDTH=dw, FORMAT=fmt,
+                          direction=direction)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("xser", ["NEW", "OLD"])
+def test_parity_nfft20_taylor_extension(ib, oracle, xser):
+    """BASELINE config c4 shape (one frame): 2^20 points, Taylor twiddles on STAGE 11..19."""
+    got, want = _run_both(ib, oracle, 1, seed=20, via="device", NFFT=20, DATA_WIDTH=16, FORMAT=0, XSER=xser)
+    assert np.array_equal(got, want)
+
+
+def test_parity_c2_sample(ib, oracle):
+    """BASELINE config c2 generics, 256 frames, device path."""
+    got, want = _run_both(ib, oracle, 256, seed=0x696E7466, via="device", NFFT=12, DATA_WIDTH=16, FORMAT=0)
+    assert np.array_equal(got, want)
+
+
+def test_parity_c5_sample(ib, oracle):
+    """BASELINE config c5 generics (8192-pt 18-bit DIT), scaled and unscaled."""
+    for fmt in (0, 1):
+        got, want = _run_both(ib, oracle, 64, seed=5 + fmt, via="device", NFFT=13, DATA_WIDTH=18, FORMAT=fmt,
+                              direction=1)
+        assert np.array_equal(got, want)
+
+
+def test_use_fly_bypass(ib, oracle):
+    for fmt in (0, 1):
+        got, want = _run_both(ib, oracle, 5, seed=3, NFFT=9, DATA_WIDTH=12, FORMAT=fmt, USE_FLY=0)
+        assert np.array_equal(got, want)
+
+
+def test_ragged_batches_and_inplace(ib, oracle):
+    """Batches that do not fill the last tile, and d_in == d_out."""
+    for nfft, batch in ((3, 1), (3, 513), (5, 129), (9, 7), (11, 3)):
+        got, want = _run_both(ib, oracle, batch, seed=batch, via="device", NFFT=nfft, DATA_WIDTH=16, FORMAT=0)
+        assert np.array_equal(got, want), (nfft, batch)
+    g = ib.Generics(NFFT=10, DATA_WIDTH=16, FORMAT=0)
+    x = oracle.fill_random(11 * 1024 * 2, 16, 77).reshape(11, 1024, 2)
+    core = ib.Core(g, 11, 0)
+    d = torch.from_numpy(x).cuda()
+    core.exec(d, d)
+    assert np.array_equal(d.cpu().numpy(), oracle.batch(oracle.generics(10), x))
+
+
+def test_invalid_generics_fail_like_elaboration(ib):
+    for kw in (dict(NFFT=2), dict(NFFT=21), dict(TWDL_WIDTH=28), dict(TWDL_WIDTH=26, XSER="OLD"), dict(DATA_WIDTH=7),
+               dict(FORMAT=1, RNDMODE=1), dict(TWDL_WIDTH=20, DATA_WIDTH=53, FORMAT=0)):
+        base = dict(NFFT=8, DATA_WIDTH=16, TWDL_WIDTH=16, FORMAT=0, RNDMODE=0)
+        base.update(kw)
+        with pytest.raises(ib.IntfftError) as ei:
+            ib.Core(ib.Generics(**base), 4, 0)
+        assert ei.value.status == -1, kw
+    with pytest.raises(ib.IntfftError) as ei:
+        ib.Core(ib.Generics(NFFT=10, DATA_WIDTH=60, FORMAT=1), 4, 0)
+    assert ei.value.status == -4
+
+
+def test_device_stimulus_and_checksum_match_oracle(ib, oracle):
+    for width, dt in ((16, torch.int16), (18, torch.int32), (40, torch.int64)):
+        d = torch.empty(100003, dtype=dt, device="cuda")
+        ib.fill_random(d, width, 0x696E7466)
+        h = oracle.fill_random(100003, width, 0x696E7466)
+        assert np.array_equal(d.cpu().numpy(), h)
+        assert ib.checksum(d) == oracle.checksum(h)
+
+
+@pytest.mark.parametrize("nfft", [3, 4, 7, 10, 12, 13, 16])
+def test_bitrev_order(ib, oracle, nfft):
+    for dt in (np.int16, np.int32, np.int64):
+        batch = 3
+        x = np.arange(batch * (1 << nfft) * 2, dtype=np.int64).astype(dt).reshape(batch, 1 << nfft, 2)
+        got = ib.bitrev_order(torch.from_numpy(x).cuda(), nfft).cpu().numpy()
+        assert np.array_equal(got, oracle.bitrev(nfft, x))
+
+
+def test_fft_ifft_pair_roundtrip_full_c2_batch(ib, oracle):
+    """Size-independent property at the full c2 size (65536 x 4096): FFT then IFFT returns x / N
+    within the truncation bias; plus a checksum-of-frames comparison with the oracle on a sample."""
+    nfft, batch = 12, 65536
+    n = 1 << nfft
+    g = ib.Generics(NFFT=nfft, DATA_WIDTH=16, FORMAT=0)
+    fwd, inv = ib.Core(g, batch, 0), ib.Core(g, batch, 1)
+    x = fwd.new_input()
+    ib.fill_random(x, 15, 99)                      # 15-bit amplitude: sqrt(2) headroom, no wrap
+    y = fwd.exec(x)
+    z = inv.exec(y)
+    err = z.to(torch.float32) - x.to(torch.float32) / n
+    assert float(err.abs().max()) < 24.0
+    assert float(err.pow(2).mean().sqrt()) < 3.0
+    # sampled frames against the oracle, bit-exact
+    og = oracle.generics(nfft)
+    for f in (0, 1, 4095, 32768, 65535):
+        want = oracle.batch(og, x[f].cpu().numpy()[None])
+        assert np.array_equal(y[f].cpu().numpy()[None], want)
+    fwd.close(); inv.close()
