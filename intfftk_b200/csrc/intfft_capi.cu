@@ -144,12 +144,19 @@ int upload_twiddles(Plan &pl)
     }
     if (cudaMalloc(&pl.d_tw, cnt * sizeof(int2)) != cudaSuccess) return INTFFT_ENOMEM;
     if (cudaMemcpy(pl.d_tw, tab.data(), cnt * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) return INTFFT_ECUDA;
-    if (pl.g.twdl_width <= 16) {
-        std::vector<uint32_t> t16(cnt);
-        for (size_t i = 0; i < cnt; ++i)
-            t16[i] = ((uint32_t)(uint16_t)tab[i].x) | ((uint32_t)(uint16_t)tab[i].y << 16);
-        if (cudaMalloc(&pl.d_tw16, cnt * sizeof(uint32_t)) != cudaSuccess) return INTFFT_ENOMEM;
-        if (cudaMemcpy(pl.d_tw16, t16.data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) return INTFFT_ECUDA;
+    if (!pl.passes.empty() && pl.passes[0].fast16) {
+        // 32-bit-product kernel: W << e with e = 33 - TWDL_WIDTH - DATA_WIDTH puts the multiplier's
+        // output slice P(DTW+TWD-2 downto TWD-1) (int_cmult_dsp48.vhd:189-190) at bits 31 .. 32-DTW
+        const int e = 33 - pl.g.twdl_width - pl.g.data_width;
+        std::vector<int2> tp(cnt);
+        for (size_t i = 0; i < cnt; ++i) tp[i] = make_int2(tab[i].x * (1 << e), tab[i].y * (1 << e));
+        for (int s = 2; s <= 3 && s < n; ++s)
+            for (int k = 0; k < (1 << s); ++k) {
+                pl.lw_r[(1 << s) - 1 + k] = tp[(1 << s) + k].x;
+                pl.lw_i[(1 << s) - 1 + k] = tp[(1 << s) + k].y;
+            }
+        if (cudaMalloc(&pl.d_twp, cnt * sizeof(int2)) != cudaSuccess) return INTFFT_ENOMEM;
+        if (cudaMemcpy(pl.d_twp, tp.data(), cnt * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) return INTFFT_ECUDA;
     }
     return INTFFT_OK;
 }
@@ -209,7 +216,7 @@ int intfft_plan_destroy(intfft_plan *p)
     if (!p) return INTFFT_EINVAL;
     DeviceGuard guard(p->device);
     cudaFree(p->d_tw);
-    cudaFree(p->d_tw16);
+    cudaFree(p->d_twp);
     cudaFree(p->scratch[0]);
     cudaFree(p->scratch[1]);
     cudaFree(p->h2d);
@@ -254,7 +261,7 @@ int intfft_exec(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream
         pd.kp.in = (i == 0) ? d_in : (pd.scratch_in >= 0 ? p->scratch[pd.scratch_in] : d_out);
         pd.kp.out = (i + 1 == p->passes.size()) ? d_out : (pd.scratch_out >= 0 ? p->scratch[pd.scratch_out] : d_out);
         pd.kp.tw = p->d_tw;
-        const int e = pd.fast16 ? launch_fast16(pd, p->mode, dit, p->d_tw16, p->num_sms, cuda_stream)
+        const int e = pd.fast16 ? launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream)
                                 : launch_tile_pass(pd, p->mode, dit, p->num_sms, cuda_stream);
         if (e) return INTFFT_ECUDA;
     }

@@ -1,6 +1,353 @@
-// placeholder until the specialised packed-16 kernel lands
+// Specialised stage-chain kernel for the headline configuration class: SCALED / TRUNCATE mode,
+// DATA_WIDTH <= 16, TWDL_WIDTH <= 16 (BASELINE c2: 4096-pt 16-bit scaled DIF), N = 2^8 .. 2^12.
+//
+// Same arithmetic as the generic kernel (intfft_tile.cu / intfft_arith.cuh) and the same reference
+// rules (int_dif2_fly.vhd:144-164, 245-318, 348-366; int_dit2_fly.vhd:142-162, 221-322;
+// int_cmult_dsp48.vhd:184-190 single-DSP slice), restructured for the integer issue ports:
+//   * samples travel as packed {re:16, im:16} words (4 B / sample in HBM and in shared memory);
+//   * all products are 32-bit: twiddles are pre-shifted by e = 33 - TWDL_WIDTH - DATA_WIDTH so that
+//     wrap_DW((P2 +- P1) >> (TWDL_WIDTH-1)) is ONE arithmetic shift of the low 32 bits of the sum
+//     of products (the slice P(DTW+TWD-2 downto TWD-1) then ends exactly at bit 31);
+//   * TRUNCATE only ever consumes A>>1 and B>>1, so (A>>1)+(B>>1) is a shift-add (LEA.HI.SX32) and
+//     (A>>1)-(B>>1) = sum - 2*(B>>1) goes to the multiply-add port (IMAD), balancing the two ports;
+//   * each thread keeps 16 samples in registers for 4 consecutive stages; the twiddles of the two
+//     upper rounds are per-thread constants hoisted out of the persistent frame loop, those of the
+//     lowest round are kernel parameters (constant bank);
+//   * DIF frames are staged HBM -> shared memory by the TMA engine (cp.async.bulk + mbarrier), one
+//     frame ahead of the arithmetic, and leave as 64-byte-per-thread vector stores;
+//   * rounds exchange through a double-buffered padded tile whose skew is additive, so every
+//     shared-memory address is "per-round base register + compile-time immediate" and every access
+//     pattern (32-bit at stride 256 / 16, 128-bit contiguous) is bank-conflict free for N = 4096.
+#include <cuda_runtime.h>
+
 #include "intfft_internal.h"
+
 namespace intfft {
-bool fast16_supported(const intfft_generics &) { return false; }
-int launch_fast16(const PassDesc &, int, bool, const uint32_t *, int, void *) { return 1; }
+
+namespace {
+
+struct Fast16Params {
+    const uint32_t *in;
+    uint32_t *out;
+    const int2 *twp;        // pre-shifted twiddles, entry (1 << s) + k
+    long long n_tiles;      // tiles of 4096 samples
+    long long total;        // batch * N samples
+    int dw, sh_full, sh_half;
+    int lw_r[16], lw_i[16]; // lowest-round twiddles: index (1 << s) - 1 + k, s = 2, 3
+};
+
+// sample index inside a 4096-sample tile -> word offset in the padded exchange tile.
+// Additive skew: 4 words per 32 samples + 16 words per 256 samples.  For disjoint bit sets
+// phys(a | b) = phys(a) + phys(b), so per-register offsets fold into instruction immediates.
+__host__ __device__ constexpr unsigned phys(unsigned i) { return i + 4u * (i >> 5) + 16u * (i >> 8); }
+constexpr unsigned kTileWords = 4864;   // >= phys(4095) + 1, multiple of 4
+
+// ---- instruction-selection helpers (inline PTX keeps the front end from re-deriving 16-bit
+// ---- value ranges and narrowing the arithmetic, and pins which issue port an op lands on) ----
+__device__ __forceinline__ int sext_lo16(uint32_t x) { int r; asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(r) : "r"(x)); return r; }
+template <int S> __device__ __forceinline__ int sra(int x) { int r; asm("shr.s32 %0, %1, %2;" : "=r"(r) : "r"(x), "n"(S)); return r; }
+__device__ __forceinline__ int msub2(int t, int x) { int r; asm("mad.lo.s32 %0, %1, -2, %2;" : "=r"(r) : "r"(t), "r"(x)); return r; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+template <bool DW16>
+__device__ __forceinline__ void unpack(uint32_t x, int dw, int &re, int &im)
+{
+    if (DW16) {
+        re = sext_lo16(x);
+        im = sra<16>((int)x);
+    } else {                                   // wrap to DATA_WIDTH bits (conv_std_logic_vector)
+        re = (int)(x << (32 - dw)) >> (32 - dw);
+        im = (int)(x << (16 - dw)) >> (32 - dw);
+    }
+}
+
+__device__ __forceinline__ uint32_t pack(int re, int im) { return __byte_perm((unsigned)re, (unsigned)im, 0x5410); }
+
+// -v for v >= 0, ~v for v < 0  (int_dif2_fly.vhd:299-303)
+__device__ __forceinline__ int negq(int v) { return (v >> 31) - v; }
+
+template <bool DIT, bool DW16>
+__device__ __forceinline__ void fly(int s, bool odd, int &ar, int &ai, int &br, int &bi, int wr, int wi,
+                                    int sh_full, int sh_half)
+{
+    if (!DIT) {
+        const int tr = sra<1>(br), ti = sra<1>(bi);
+        const int xr = sra<1>(ar) + tr, xi = sra<1>(ai) + ti;
+        const int sr = msub2(tr, xr), si = msub2(ti, xi);       // (A>>1) - (B>>1)
+        ar = xr;
+        ai = xi;
+        if (s == 0) {
+            br = sr;
+            bi = si;
+        } else if (s == 1) {
+            br = odd ? si : sr;
+            bi = odd ? negq(sr) : si;
+        } else {
+            const int pr = (int)((unsigned)sr * (unsigned)wr - (unsigned)si * (unsigned)wi);
+            const int pi = (int)((unsigned)sr * (unsigned)wi + (unsigned)si * (unsigned)wr);
+            br = DW16 ? sra<16>(pr) : (pr >> sh_full);
+            bi = DW16 ? sra<16>(pi) : (pi >> sh_full);
+        }
+    } else {
+        int hr, hi;                                             // BW >> 1
+        if (s == 0) {
+            hr = sra<1>(br);
+            hi = sra<1>(bi);
+        } else if (s == 1) {
+            hr = sra<1>(odd ? negq(bi) : br);
+            hi = sra<1>(odd ? br : bi);
+        } else {                                                // multiplier fed with swapped re / im
+            const int o_re = (int)((unsigned)bi * (unsigned)wr - (unsigned)br * (unsigned)wi);
+            const int o_im = (int)((unsigned)bi * (unsigned)wi + (unsigned)br * (unsigned)wr);
+            hi = DW16 ? sra<17>(o_re) : (o_re >> sh_half);
+            hr = DW16 ? sra<17>(o_im) : (o_im >> sh_half);
+        }
+        const int xr = sra<1>(ar) + hr, xi = sra<1>(ai) + hi;
+        br = msub2(hr, xr);
+        bi = msub2(hi, xi);
+        ar = xr;
+        ai = xi;
+    }
+}
+
+// R stages (global bits LO .. LO+R-1) on the 16 register-resident samples
+template <int LO, int R, bool DIT, bool DW16>
+__device__ __forceinline__ void round_regs(int (&re)[16], int (&im)[16], const int (&wr)[15], const int (&wi)[15],
+                                           bool tid_odd, int sh_full, int sh_half)
+{
+#pragma unroll
+    for (int step = 0; step < R; ++step) {
+        const int q = DIT ? step : R - 1 - step;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            if (m & (1 << q)) continue;
+            const int j = m & ((1 << q) - 1);
+            const int w = (1 << q) - 1 + j;
+            const bool odd = (LO == 0) ? ((m & 1) != 0) : tid_odd;    // twiddle index bit 0 (STAGE = 1 only)
+            fly<DIT, DW16>(LO + q, odd, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr[w], wi[w],
+                           sh_full, sh_half);
+        }
+    }
+}
+
+template <int NLOG2, bool DIT, bool DW16>
+__global__ void __launch_bounds__(256, 2) fast16_kernel(const __grid_constant__ Fast16Params p)
+{
+    constexpr int R0 = ((NLOG2 - 1) % 4) + 1;      // stages in the lowest round
+    constexpr int NR = 1 + (NLOG2 - R0) / 4;       // rounds; round r > 0 covers bits R0+4(r-1) .. +3
+    static_assert(NR >= 2 && NR <= 3, "supported: 2^5 .. 2^12 points");
+    constexpr bool TMA_IN = !DIT;                  // DIF: first round reads stride-256 words -> stage via TMA
+
+    // dynamic shared memory: [bar 2 x u64 | pad to 128] [work 2 x kTileWords] [stage 2 x 4096 (DIF only)]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t(*work)[kTileWords] = reinterpret_cast<uint32_t(*)[kTileWords]>(smem_raw + 128);
+    uint32_t(*stage)[4096] = reinterpret_cast<uint32_t(*)[4096]>(smem_raw + 128 + 2 * kTileWords * 4);
+
+    const unsigned tid = threadIdx.x;
+    const int sh_full = p.sh_full, sh_half = p.sh_half;
+    const bool tid_odd = tid & 1u;
+
+    if (TMA_IN) {
+        if (tid == 0) {
+            mbar_init(&bar[0], 1);
+            mbar_init(&bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0 && (long long)blockIdx.x < p.n_tiles) {
+            const long long g0 = (long long)blockIdx.x << 12;
+            const long long left = p.total - g0;
+            const uint32_t bytes = (uint32_t)(left < 4096 ? left : 4096) * 4u;
+            mbar_expect_tx(&bar[0], bytes);
+            tma_load_1d(stage[0], p.in + g0, bytes, &bar[0]);
+        }
+    }
+
+    // ---- per-thread constant twiddles of the upper rounds ----
+    int uwr[NR - 1][15], uwi[NR - 1][15];
+#pragma unroll
+    for (int r = 1; r < NR; ++r) {
+        const int lo = R0 + 4 * (r - 1);
+        const unsigned low = tid & ((1u << lo) - 1u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < (1 << q); ++j) {
+                const int2 w = __ldg(p.twp + (1u << (lo + q)) + low + ((unsigned)j << lo));
+                uwr[r - 1][(1 << q) - 1 + j] = w.x;
+                uwi[r - 1][(1 << q) - 1 + j] = w.y;
+            }
+    }
+    int lwr[15], lwi[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) { lwr[i] = p.lw_r[i]; lwi[i] = p.lw_i[i]; }
+
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        uint32_t *sm = work[it & 1];
+        const long long g0 = tile << 12;
+        const bool full = g0 + 4096 <= p.total;
+
+        if (TMA_IN) {
+            const long long nt = tile + gridDim.x;            // prefetch the next frame of this CTA
+            if (tid == 0 && nt < p.n_tiles) {
+                const long long left = p.total - (nt << 12);
+                const uint32_t bytes = (uint32_t)(left < 4096 ? left : 4096) * 4u;
+                mbar_expect_tx(&bar[(it + 1) & 1], bytes);
+                tma_load_1d(stage[(it + 1) & 1], p.in + (nt << 12), bytes, &bar[(it + 1) & 1]);
+            }
+            mbar_wait(&bar[it & 1], (it >> 1) & 1);
+        }
+
+        int re[16], im[16];
+#pragma unroll
+        for (int rr = 0; rr < NR; ++rr) {
+            const int r = DIT ? rr : NR - 1 - rr;                 // DIF walks the bits downwards
+            const int lo = r == 0 ? 0 : R0 + 4 * (r - 1);
+            const int R = r == 0 ? R0 : 4;
+            const bool first = rr == 0, last = rr == NR - 1;
+            const unsigned base = (tid & ((1u << lo) - 1u)) | ((tid >> lo) << (lo + R));
+            const unsigned pbase = phys(base);
+
+            // ---- fetch 16 samples ----
+            if (r == 0 && R0 == 4) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 v;
+                    if (first) {                                  // DIT: straight from HBM, 64 B per thread
+                        const long long gi = g0 + 16 * tid + 4 * c;
+                        v = (full || gi < p.total) ? __ldg(reinterpret_cast<const uint4 *>(p.in + gi)) : make_uint4(0, 0, 0, 0);
+                    } else {
+                        v = *reinterpret_cast<const uint4 *>(sm + pbase + phys(4 * c));
+                    }
+                    unpack<DW16>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
+                    unpack<DW16>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
+                    unpack<DW16>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
+                    unpack<DW16>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
+                    uint32_t x;
+                    if (first && TMA_IN) x = stage[it & 1][base + off];
+                    else if (first) x = (full || (g0 + base + off) < p.total) ? __ldg(p.in + g0 + base + off) : 0u;
+                    else x = sm[pbase + phys(off)];
+                    unpack<DW16>(x, p.dw, re[m], im[m]);
+                }
+            }
+
+            // ---- butterflies ----
+            if (r == 0) round_regs<0, R0, DIT, DW16>(re, im, lwr, lwi, tid_odd, sh_full, sh_half);
+            else if (r == 1) round_regs<R0, 4, DIT, DW16>(re, im, uwr[0], uwi[0], tid_odd, sh_full, sh_half);
+            else round_regs<R0 + 4, 4, DIT, DW16>(re, im, uwr[NR - 2], uwi[NR - 2], tid_odd, sh_full, sh_half);
+
+            // ---- hand the samples on: to the exchange tile, or to HBM after the last round ----
+            if (r == 0 && R0 == 4) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 v = make_uint4(pack(re[4 * c], im[4 * c]), pack(re[4 * c + 1], im[4 * c + 1]),
+                                               pack(re[4 * c + 2], im[4 * c + 2]), pack(re[4 * c + 3], im[4 * c + 3]));
+                    if (last) {
+                        const long long gi = g0 + 16 * tid + 4 * c;
+                        if (full || gi < p.total) *reinterpret_cast<uint4 *>(p.out + gi) = v;
+                    } else {
+                        *reinterpret_cast<uint4 *>(sm + pbase + phys(4 * c)) = v;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
+                    const uint32_t x = pack(re[m], im[m]);
+                    if (last) { if (full || (g0 + base + off) < p.total) p.out[g0 + base + off] = x; }
+                    else sm[pbase + phys(off)] = x;
+                }
+            }
+            if (!last) __syncthreads();
+        }
+    }
+}
+
+template <int NLOG2, bool DIT, bool DW16>
+cudaError_t launch_k(const Fast16Params &p, int grid, cudaStream_t st)
+{
+    const int smem = 128 + 2 * kTileWords * 4 + (DIT ? 0 : 2 * 4096 * 4);
+    auto k = fast16_kernel<NLOG2, DIT, DW16>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int NLOG2>
+cudaError_t launch_n(const Fast16Params &p, bool dit, bool dw16, int grid, cudaStream_t st)
+{
+    if (!dit) return dw16 ? launch_k<NLOG2, false, true>(p, grid, st) : launch_k<NLOG2, false, false>(p, grid, st);
+    return dw16 ? launch_k<NLOG2, true, true>(p, grid, st) : launch_k<NLOG2, true, false>(p, grid, st);
+}
+
+}  // namespace
+
+bool fast16_supported(const intfft_generics &g)
+{
+    return g.format == 0 && g.rndmode == 0 && g.use_fly == 1 && g.data_width <= 16 && g.twdl_width <= 16 &&
+           g.nfft_log2 >= 8 && g.nfft_log2 <= 12;
+}
+
+int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
+                  int num_sms, void *stream)
+{
+    (void)mode;
+    Fast16Params p{};
+    p.in = reinterpret_cast<const uint32_t *>(pd.kp.in);
+    p.out = reinterpret_cast<uint32_t *>(pd.kp.out);
+    p.twp = twp;
+    p.total = pd.kp.total;
+    p.n_tiles = (pd.kp.total + 4095) >> 12;
+    p.dw = pd.kp.dw;
+    p.sh_full = 32 - p.dw;
+    p.sh_half = 33 - p.dw;
+    for (int i = 0; i < 16; ++i) { p.lw_r[i] = lw_r[i]; p.lw_i[i] = lw_i[i]; }
+    long long grid = 2ll * num_sms;
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    if (grid < 1) grid = 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool dw16 = p.dw == 16;
+    cudaError_t e;
+    switch (pd.kp.n) {
+    case 8: e = launch_n<8>(p, dit, dw16, (int)grid, st); break;
+    case 9: e = launch_n<9>(p, dit, dw16, (int)grid, st); break;
+    case 10: e = launch_n<10>(p, dit, dw16, (int)grid, st); break;
+    case 11: e = launch_n<11>(p, dit, dw16, (int)grid, st); break;
+    case 12: e = launch_n<12>(p, dit, dw16, (int)grid, st); break;
+    default: e = cudaErrorInvalidValue; break;
+    }
+    count_launch();
+    return (int)e;
+}
+
 }  // namespace intfft

@@ -67,7 +67,8 @@ struct Plan {
     int in_width, out_width, in_sb, out_sb;
     std::vector<PassDesc> passes;
     int2 *d_tw = nullptr;        // device twiddle table (int32 pairs)
-    uint32_t *d_tw16 = nullptr;  // device twiddle table, packed int16 pairs (TW <= 16 only)
+    int2 *d_twp = nullptr;       // twiddles pre-shifted for the 32-bit-product kernel (fast16 plans only)
+    int lw_r[16] = {0}, lw_i[16] = {0};  // its lowest-round twiddles (stages 2, 3)
     void *scratch[2] = {nullptr, nullptr};
     size_t scratch_bytes[2] = {0, 0};
     void *h2d = nullptr, *d2h = nullptr;  // device staging for intfft_exec_host
@@ -76,7 +77,8 @@ struct Plan {
 
 // kernels (intfft_tile.cu / intfft_fast16.cu / intfft_util.cu); all return cudaError_t as int
 int launch_tile_pass(const PassDesc &pd, int mode, bool dit, int num_sms, void *stream);
-int launch_fast16(const PassDesc &pd, int mode, bool dit, const uint32_t *tw16, int num_sms, void *stream);
+int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
+                  int num_sms, void *stream);
 bool fast16_supported(const intfft_generics &g);
 int launch_bypass(const void *in, void *out, long long n_scalars, int in_sb, int out_sb, int dw,
                   int zero_extend, void *stream);

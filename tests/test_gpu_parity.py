@@ -80,6 +80,31 @@ def test_parity_widths_and_multiplier_variants(ib, oracle, dw, tw, xser, directi
         assert np.array_equal(got, want), (fmt, rnd)
 
 
+@pytest.mark.parametrize("nfft", [8, 9, 10, 11, 12])
+@pytest.mark.parametrize("direction", [0, 1])
+def test_parity_packed16_kernel_widths(ib, oracle, nfft, direction):
+    """The specialised packed-16 kernel (scaled TRUNCATE, DW <= 16, TW <= 16) at narrower widths,
+    ragged batches (last tile only partly filled) and both XSER settings."""
+    for dw, tw, xser in ((16, 16, "OLD"), (12, 16, "NEW"), (16, 12, "NEW"), (10, 9, "OLD"), (8, 8, "NEW"), (15, 16, "NEW")):
+        batch = (3 << (12 - nfft)) + 1
+        got, want = _run_both(ib, oracle, batch, seed=nfft + dw, via="device", NFFT=nfft, DATA_WIDTH=dw,
+                              TWDL_WIDTH=tw, FORMAT=0, RNDMODE=0, XSER=xser, direction=direction)
+        assert np.array_equal(got, want), (dw, tw, xser)
+
+
+def test_packed16_kernel_matches_generic_kernel(ib, oracle, monkeypatch):
+    """Same plan through both device kernels (INTFFT_DISABLE_FAST16 selects the generic one)."""
+    g = ib.Generics(NFFT=12, DATA_WIDTH=16, FORMAT=0)
+    x = torch.from_numpy(oracle.fill_random(40 * 4096 * 2, 16, 123).reshape(40, 4096, 2)).cuda()
+    for direction in (0, 1):
+        fast = ib.Core(g, 40, direction)
+        monkeypatch.setenv("INTFFT_DISABLE_FAST16", "1")
+        slow = ib.Core(g, 40, direction)
+        monkeypatch.delenv("INTFFT_DISABLE_FAST16")
+        assert torch.equal(fast.exec(x), slow.exec(x))
+        fast.close(); slow.close()
+
+
 @pytest.mark.parametrize("nfft,dw,fmt,direction", [(14, 16, 0, 0), (14, 16, 0, 1), (15, 18, 1, 0), (16, 24, 1, 0),
                                                    (16, 16, 0, 1), (17, 16, 0, 0), (18, 12, 1, 1)])
 def test_parity_multipass(ib, oracle, nfft, dw, fmt, direction):
