@@ -131,10 +131,7 @@ def twiddles(g: Generics, stage: int):
     return re, im
 
 
-def shard_range(batch: int, rank: int, world: int) -> tuple[int, int]:
-    """Frames [lo, hi) owned by `rank` when a batch is split over `world` GPUs (no exchange step:
-    frames are independent)."""
-    return batch * rank // world, batch * (rank + 1) // world
+from .sharding import shard_range  # noqa: E402,F401  (re-exported)
 
 
 class Core:

@@ -221,6 +221,9 @@ int intfft_plan_destroy(intfft_plan *p)
     cudaFree(p->scratch[1]);
     cudaFree(p->h2d);
     cudaFree(p->d2h);
+    for (void *e : p->ev_in) cudaEventDestroy((cudaEvent_t)e);
+    for (void *e : p->ev_k) cudaEventDestroy((cudaEvent_t)e);
+    if (p->s_in) { cudaStreamDestroy((cudaStream_t)p->s_in); cudaStreamDestroy((cudaStream_t)p->s_k); cudaStreamDestroy((cudaStream_t)p->s_out); }
     delete p;
     return INTFFT_OK;
 }
@@ -243,15 +246,13 @@ int intfft_query(const intfft_plan *p, intfft_layout *l)
     return INTFFT_OK;
 }
 
-int intfft_exec(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream)
+// run `frames` frames (<= plan batch) starting at d_in / d_out
+static int exec_frames(intfft_plan *p, const void *d_in, void *d_out, long long frames, void *cuda_stream)
 {
-    if (!p || !d_in || !d_out) return INTFFT_EINVAL;
-    if (d_in == d_out && p->in_sb != p->out_sb) return INTFFT_EINVAL;
-    DeviceGuard guard(p->device);
-    if (!guard.ok) return INTFFT_ECUDA;
-    const long long n_scalars = (p->batch << p->g.nfft_log2) * 2;
+    const int n = p->g.nfft_log2;
+    const long long total = frames << n;
     if (!p->g.use_fly) {
-        const int e = launch_bypass(d_in, d_out, n_scalars, p->in_sb, p->out_sb, p->g.data_width,
+        const int e = launch_bypass(d_in, d_out, total * 2, p->in_sb, p->out_sb, p->g.data_width,
                                     p->g.format, cuda_stream);
         return e ? INTFFT_ECUDA : INTFFT_OK;
     }
@@ -261,6 +262,8 @@ int intfft_exec(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream
         pd.kp.in = (i == 0) ? d_in : (pd.scratch_in >= 0 ? p->scratch[pd.scratch_in] : d_out);
         pd.kp.out = (i + 1 == p->passes.size()) ? d_out : (pd.scratch_out >= 0 ? p->scratch[pd.scratch_out] : d_out);
         pd.kp.tw = p->d_tw;
+        pd.kp.total = total;
+        pd.kp.n_tiles = pd.kp.c > 0 ? (frames << (n - pd.kp.L)) : ((total + (1ll << pd.kp.L) - 1) >> pd.kp.L);
         const int e = pd.fast16 ? launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream)
                                 : launch_tile_pass(pd, p->mode, dit, p->num_sms, cuda_stream);
         if (e) return INTFFT_ECUDA;
@@ -268,6 +271,17 @@ int intfft_exec(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream
     return INTFFT_OK;
 }
 
+int intfft_exec(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream)
+{
+    if (!p || !d_in || !d_out) return INTFFT_EINVAL;
+    if (d_in == d_out && p->in_sb != p->out_sb) return INTFFT_EINVAL;
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return INTFFT_ECUDA;
+    return exec_frames(p, d_in, d_out, p->batch, cuda_stream);
+}
+
+// Host buffers: the batch is cut into chunks that flow through three streams (H2D copy, kernels,
+// D2H copy), so the two PCIe directions and the SMs work at the same time.
 int intfft_exec_host(intfft_plan *p, const void *h_in, void *h_out)
 {
     if (!p || !h_in || !h_out) return INTFFT_EINVAL;
@@ -277,11 +291,43 @@ int intfft_exec_host(intfft_plan *p, const void *h_in, void *h_out)
     intfft_query(p, &l);
     if (!p->h2d && cudaMalloc(&p->h2d, (size_t)l.in_bytes) != cudaSuccess) return INTFFT_ENOMEM;
     if (!p->d2h && cudaMalloc(&p->d2h, (size_t)l.out_bytes) != cudaSuccess) return INTFFT_ENOMEM;
-    if (cudaMemcpyAsync(p->h2d, h_in, (size_t)l.in_bytes, cudaMemcpyHostToDevice, 0) != cudaSuccess) return INTFFT_ECUDA;
-    const int st = intfft_exec(p, p->h2d, p->d2h, nullptr);
-    if (st) return st;
-    if (cudaMemcpyAsync(h_out, p->d2h, (size_t)l.out_bytes, cudaMemcpyDeviceToHost, 0) != cudaSuccess) return INTFFT_ECUDA;
-    return cudaStreamSynchronize(0) == cudaSuccess ? INTFFT_OK : INTFFT_ECUDA;
+    const long long in_per_frame = l.in_bytes / p->batch, out_per_frame = l.out_bytes / p->batch;
+    long long chunk = (32ll << 20) / in_per_frame;          // ~32 MiB of input per chunk
+    if (chunk < 1) chunk = 1;
+    const long long n_chunks = (p->batch + chunk - 1) / chunk;
+    if (!p->s_in) {
+        cudaStream_t a, b, c;
+        if (cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c, cudaStreamNonBlocking) != cudaSuccess)
+            return INTFFT_ECUDA;
+        p->s_in = a; p->s_k = b; p->s_out = c;
+    }
+    while ((long long)p->ev_in.size() < n_chunks) {
+        cudaEvent_t e1, e2;
+        if (cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess)
+            return INTFFT_ECUDA;
+        p->ev_in.push_back(e1);
+        p->ev_k.push_back(e2);
+    }
+    cudaStream_t s_in = (cudaStream_t)p->s_in, s_k = (cudaStream_t)p->s_k, s_out = (cudaStream_t)p->s_out;
+    for (long long c = 0; c < n_chunks; ++c) {
+        const long long f0 = c * chunk, nf = (f0 + chunk <= p->batch) ? chunk : p->batch - f0;
+        char *di = (char *)p->h2d + f0 * in_per_frame, *dout = (char *)p->d2h + f0 * out_per_frame;
+        if (cudaMemcpyAsync(di, (const char *)h_in + f0 * in_per_frame, (size_t)(nf * in_per_frame),
+                            cudaMemcpyHostToDevice, s_in) != cudaSuccess) return INTFFT_ECUDA;
+        cudaEventRecord((cudaEvent_t)p->ev_in[c], s_in);
+        cudaStreamWaitEvent(s_k, (cudaEvent_t)p->ev_in[c], 0);
+        const int st = exec_frames(p, di, dout, nf, s_k);
+        if (st) return st;
+        cudaEventRecord((cudaEvent_t)p->ev_k[c], s_k);
+        cudaStreamWaitEvent(s_out, (cudaEvent_t)p->ev_k[c], 0);
+        if (cudaMemcpyAsync((char *)h_out + f0 * out_per_frame, dout, (size_t)(nf * out_per_frame),
+                            cudaMemcpyDeviceToHost, s_out) != cudaSuccess) return INTFFT_ECUDA;
+    }
+    if (cudaStreamSynchronize(s_out) != cudaSuccess) return INTFFT_ECUDA;
+    return cudaGetLastError() == cudaSuccess ? INTFFT_OK : INTFFT_ECUDA;
 }
 
 int intfft_twiddles(const intfft_generics *g, int stage, int32_t *h_re, int32_t *h_im)

@@ -41,6 +41,7 @@ struct Fast16Params {
 // phys(a | b) = phys(a) + phys(b), so per-register offsets fold into instruction immediates.
 __host__ __device__ constexpr unsigned phys(unsigned i) { return i + 4u * (i >> 5) + 16u * (i >> 8); }
 constexpr unsigned kTileWords = 4864;   // >= phys(4095) + 1, multiple of 4
+constexpr unsigned kSmemHead = 128 + 15 * 16 * 8;   // barriers + middle-round twiddle table
 
 // ---- instruction-selection helpers (inline PTX keeps the front end from re-deriving 16-bit
 // ---- value ranges and narrowing the arithmetic, and pins which issue port an op lands on) ----
@@ -133,9 +134,9 @@ __device__ __forceinline__ void fly(int s, bool odd, int &ar, int &ai, int &br, 
 }
 
 // R stages (global bits LO .. LO+R-1) on the 16 register-resident samples
-template <int LO, int R, bool DIT, bool DW16>
-__device__ __forceinline__ void round_regs(int (&re)[16], int (&im)[16], const int (&wr)[15], const int (&wi)[15],
-                                           bool tid_odd, int sh_full, int sh_half)
+template <int LO, int R, bool DIT, bool DW16, typename TW>
+__device__ __forceinline__ void round_regs(int (&re)[16], int (&im)[16], const TW &tw, bool tid_odd, int sh_full,
+                                           int sh_half)
 {
 #pragma unroll
     for (int step = 0; step < R; ++step) {
@@ -146,25 +147,47 @@ __device__ __forceinline__ void round_regs(int (&re)[16], int (&im)[16], const i
             const int j = m & ((1 << q) - 1);
             const int w = (1 << q) - 1 + j;
             const bool odd = (LO == 0) ? ((m & 1) != 0) : tid_odd;    // twiddle index bit 0 (STAGE = 1 only)
-            fly<DIT, DW16>(LO + q, odd, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr[w], wi[w],
-                           sh_full, sh_half);
+            int wr = 0, wi = 0;
+            if (LO + q >= 2) tw(w, wr, wi);
+            fly<DIT, DW16>(LO + q, odd, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi, sh_full, sh_half);
         }
     }
 }
 
-template <int NLOG2, bool DIT, bool DW16>
-__global__ void __launch_bounds__(256, 2) fast16_kernel(const __grid_constant__ Fast16Params p)
+// twiddle sources for round_regs
+struct TwRegs {
+    const int (&r)[15];
+    const int (&i)[15];
+    __device__ __forceinline__ void operator()(int w, int &wr, int &wi) const { wr = r[w]; wi = i[w]; }
+};
+struct TwSmem {          // table[w][tid & 15] of pre-shifted (re, im); one LDS.64 per butterfly
+    const int2 *t;
+    __device__ __forceinline__ void operator()(int w, int &wr, int &wi) const
+    {
+        const int2 v = t[w * 16];
+        wr = v.x;
+        wi = v.y;
+    }
+};
+
+// MIDSM: keep the middle round's 15 twiddles in a 1920-byte shared table instead of 30 registers, which
+// brings the kernel under 85 registers so that three CTAs (24 warps) fit on one SM.
+template <int NLOG2, bool DIT, bool DW16, bool MIDSM>
+__global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid_constant__ Fast16Params p)
 {
     constexpr int R0 = ((NLOG2 - 1) % 4) + 1;      // stages in the lowest round
     constexpr int NR = 1 + (NLOG2 - R0) / 4;       // rounds; round r > 0 covers bits R0+4(r-1) .. +3
     static_assert(NR >= 2 && NR <= 3, "supported: 2^5 .. 2^12 points");
     constexpr bool TMA_IN = !DIT;                  // DIF: first round reads stride-256 words -> stage via TMA
 
-    // dynamic shared memory: [bar 2 x u64 | pad to 128] [work 2 x kTileWords] [stage 2 x 4096 (DIF only)]
+    static_assert(!MIDSM || (NR == 3 && R0 == 4), "MIDSM is for the three-round 4+4+4 schedule");
+    // dynamic shared memory: [bar 2 x u64 | pad to 128] [mid twiddles 15 x 16 x int2] [work 2 x kTileWords]
+    //                        [stage 2 x 4096 (DIF only)]
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    uint32_t(*work)[kTileWords] = reinterpret_cast<uint32_t(*)[kTileWords]>(smem_raw + 128);
-    uint32_t(*stage)[4096] = reinterpret_cast<uint32_t(*)[4096]>(smem_raw + 128 + 2 * kTileWords * 4);
+    int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);
+    uint32_t(*work)[kTileWords] = reinterpret_cast<uint32_t(*)[kTileWords]>(smem_raw + kSmemHead);
+    uint32_t(*stage)[4096] = reinterpret_cast<uint32_t(*)[4096]>(smem_raw + kSmemHead + 2 * kTileWords * 4);
 
     const unsigned tid = threadIdx.x;
     const int sh_full = p.sh_full, sh_half = p.sh_half;
@@ -187,9 +210,19 @@ __global__ void __launch_bounds__(256, 2) fast16_kernel(const __grid_constant__ 
     }
 
     // ---- per-thread constant twiddles of the upper rounds ----
+    if (MIDSM) {                                   // table[w][lo4], w = (1 << q) - 1 + j, stage = R0 + q
+        if (tid < 240) {
+            const int w = tid >> 4, lo4 = tid & 15;
+            const int q = w >= 7 ? 3 : (w >= 3 ? 2 : (w >= 1 ? 1 : 0));
+            const int j = w - ((1 << q) - 1);
+            midtw[w * 16 + lo4] = __ldg(p.twp + (1u << (R0 + q)) + lo4 + ((unsigned)j << R0));
+        }
+        __syncthreads();
+    }
     int uwr[NR - 1][15], uwi[NR - 1][15];
 #pragma unroll
     for (int r = 1; r < NR; ++r) {
+        if (MIDSM && r == 1) continue;
         const int lo = R0 + 4 * (r - 1);
         const unsigned low = tid & ((1u << lo) - 1u);
 #pragma unroll
@@ -261,9 +294,10 @@ __global__ void __launch_bounds__(256, 2) fast16_kernel(const __grid_constant__ 
             }
 
             // ---- butterflies ----
-            if (r == 0) round_regs<0, R0, DIT, DW16>(re, im, lwr, lwi, tid_odd, sh_full, sh_half);
-            else if (r == 1) round_regs<R0, 4, DIT, DW16>(re, im, uwr[0], uwi[0], tid_odd, sh_full, sh_half);
-            else round_regs<R0 + 4, 4, DIT, DW16>(re, im, uwr[NR - 2], uwi[NR - 2], tid_odd, sh_full, sh_half);
+            if (r == 0) round_regs<0, R0, DIT, DW16>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
+            else if (r == 1 && MIDSM) round_regs<R0, 4, DIT, DW16>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
+            else if (r == 1) round_regs<R0, 4, DIT, DW16>(re, im, TwRegs{uwr[0], uwi[0]}, tid_odd, sh_full, sh_half);
+            else round_regs<R0 + 4, 4, DIT, DW16>(re, im, TwRegs{uwr[NR - 2], uwi[NR - 2]}, tid_odd, sh_full, sh_half);
 
             // ---- hand the samples on: to the exchange tile, or to HBM after the last round ----
             if (r == 0 && R0 == 4) {
@@ -287,7 +321,14 @@ __global__ void __launch_bounds__(256, 2) fast16_kernel(const __grid_constant__ 
                     else sm[pbase + phys(off)] = x;
                 }
             }
-            if (!last) __syncthreads();
+            // The hand-over between the two LOWEST rounds of the 4+4+4 schedule stays inside a warp
+            // (round bits 7..4 <-> 3..0 both keep tid >> 5 fixed), so a warp barrier is enough there;
+            // the double-buffered tile makes one CTA barrier per frame sufficient for reuse safety.
+            if (!last) {
+                const bool warp_local = (NR == 3 && R0 == 4) && ((DIT && rr == 0) || (!DIT && rr == 1));
+                if (warp_local) __syncwarp();
+                else __syncthreads();
+            }
         }
     }
 }
@@ -295,8 +336,9 @@ __global__ void __launch_bounds__(256, 2) fast16_kernel(const __grid_constant__ 
 template <int NLOG2, bool DIT, bool DW16>
 cudaError_t launch_k(const Fast16Params &p, int grid, cudaStream_t st)
 {
-    const int smem = 128 + 2 * kTileWords * 4 + (DIT ? 0 : 2 * 4096 * 4);
-    auto k = fast16_kernel<NLOG2, DIT, DW16>;
+    const int smem = kSmemHead + 2 * kTileWords * 4 + (DIT ? 0 : 2 * 4096 * 4);
+    constexpr bool MIDSM = (NLOG2 == 12);
+    auto k = fast16_kernel<NLOG2, DIT, DW16, MIDSM>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, smem, st>>>(p);
@@ -332,7 +374,7 @@ int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const
     p.sh_full = 32 - p.dw;
     p.sh_half = 33 - p.dw;
     for (int i = 0; i < 16; ++i) { p.lw_r[i] = lw_r[i]; p.lw_i[i] = lw_i[i]; }
-    long long grid = 2ll * num_sms;
+    long long grid = (pd.kp.n == 12 ? 3ll : 2ll) * num_sms;
     if (grid > p.n_tiles) grid = p.n_tiles;
     if (grid < 1) grid = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

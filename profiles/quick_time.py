@@ -1,0 +1,32 @@
+"""Quick device-only timing of one plan (used while tuning kernels; not the bench contract)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import intfftk_b200 as ib
+
+def time_plan(batch, steps=50, direction=0, **gk):
+    g = ib.Generics(**gk)
+    core = ib.Core(g, batch, direction)
+    x, y = core.new_input(), core.new_output()
+    ib.fill_random(x, g.DATA_WIDTH, 1)
+    for _ in range(5):
+        core.exec(x, y)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        core.exec(x, y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n = 1 << g.NFFT
+    print(f"NFFT={g.NFFT} DW={g.DATA_WIDTH} fmt={g.FORMAT} dir={direction} batch={batch}: {ms*1e3:9.1f} us  "
+          f"{batch*n/ms/1e6:10.1f} Gsamples/s", flush=True)
+    core.close()
+
+if __name__ == "__main__":
+    for b in (296, 444, 888, 4440, 65536):
+        time_plan(b, NFFT=12, DATA_WIDTH=16, FORMAT=0)
+    time_plan(65536, direction=1, NFFT=12, DATA_WIDTH=16, FORMAT=0)
+    for n in (8, 9, 10, 11):
+        time_plan(65536 << (12 - n), NFFT=n, DATA_WIDTH=16, FORMAT=0)

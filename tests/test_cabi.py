@@ -1,0 +1,96 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/intfft.h declares, validates generics like the reference elaborates them, and its twiddle
+generator agrees with the oracle.  No compute call is made (there is no GPU here and no fallback)."""
+import ctypes
+import itertools
+import os
+import re
+
+import numpy as np
+import pytest
+
+import intfftk_b200 as ib
+from oracle import c_oracle as co
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "intfft.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(intfft_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ib.lib()
+    names = _declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"libintfft_b200.so does not export {n}"
+    assert lib.intfft_version() >= 100
+    assert b"elaborate" in lib.intfft_strerror(-1)
+
+
+def test_header_is_plain_c():
+    """The header must compile as C (no torch / C++ types in the signatures)."""
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c")
+        open(src, "w").write('#include "intfft.h"\nint main(void){intfft_generics g; (void)g; return 0;}\n')
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), src])
+
+
+def test_validate_agrees_with_oracle_everywhere():
+    n_checked = 0
+    for nfft, dw, tw, fmt, rnd, xser, direction in itertools.product(
+            (2, 3, 10, 13, 19, 20, 21), (7, 8, 16, 18, 26, 28, 36, 44, 45, 52, 53, 60, 64),
+            (7, 8, 16, 18, 19, 25, 26, 27, 28), (0, 1), (0, 1), ("OLD", "NEW"), (0, 1)):
+        g = ib.Generics(NFFT=nfft, DATA_WIDTH=dw, TWDL_WIDTH=tw, FORMAT=fmt, RNDMODE=rnd, XSER=xser)
+        want = co.validate(co.generics(nfft, dw, tw, fmt, rnd, 1 if xser == "NEW" else 0, 1, direction))
+        assert ib.validate(g, direction) == want, (nfft, dw, tw, fmt, rnd, xser, direction)
+        n_checked += 1
+    assert n_checked > 5000
+
+
+@pytest.mark.parametrize("tw,xser", [(8, "NEW"), (16, "NEW"), (16, "OLD"), (17, "NEW"), (18, "OLD"), (24, "NEW"),
+                                     (25, "OLD"), (27, "NEW")])
+def test_twiddle_readback_matches_oracle(tw, xser):
+    """intfft_twiddles == what rom_twiddle_int / row_twiddle_tay stream (oracle restatement)."""
+    for stage in range(2, 20):
+        re_, im_ = ib.twiddles(ib.Generics(TWDL_WIDTH=tw, XSER=xser), stage)
+        r2, i2 = co.twiddle_table(co.generics(12, twdl_width=tw, xser=1 if xser == "NEW" else 0), stage)
+        assert np.array_equal(re_, r2) and np.array_equal(im_, i2), stage
+
+
+def test_plan_create_without_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(ib.IntfftError) as ei:
+        ib.int_fftNk(4, NFFT=8, FORMAT=0)
+    assert ei.value.status == -2          # INTFFT_ECUDA: no fallback path exists
+
+
+def test_bad_arguments():
+    lib = ib.lib()
+    assert lib.intfft_validate(None) == -1
+    assert lib.intfft_plan_destroy(None) == -1
+    assert lib.intfft_query(None, None) == -1
+    assert lib.intfft_exec(None, None, None, None) == -1
+    assert lib.intfft_twiddles(None, 5, None, None) == -1
+    with pytest.raises(ib.IntfftError):
+        ib.twiddles(ib.Generics(), 1)
+    with pytest.raises(ib.IntfftError):
+        ib.Generics(XSER="ULTRA").c_struct(0)
+
+
+def test_mode_strings_and_generics_mirror():
+    assert ib.set_mode("UNSCALED") == (1, 0)
+    assert ib.set_mode("ROUNDING") == (0, 1)
+    assert ib.set_mode("TRUNCATE") == (0, 0)
+    with pytest.raises(ValueError):
+        ib.set_mode("SATURATE")
+    g = ib.Generics(NFFT=16, DATA_WIDTH=24, FORMAT=1)
+    assert g.out_width == 40
+    c = g.c_struct(1)
+    assert (c.nfft_log2, c.data_width, c.twdl_width, c.format, c.xser, c.direction) == (16, 24, 16, 1, 1, 1)
