@@ -18,12 +18,20 @@ template <typename T> struct LaneBits;
 template <> struct LaneBits<int32_t> { static constexpr int bits = 32; using U = uint32_t; };
 template <> struct LaneBits<int64_t> { static constexpr int bits = 64; using U = uint64_t; };
 
-// keep the low w bits, sign-extended (a VHDL slice)
-template <typename T> __device__ __forceinline__ T wrapw(T v, int w)
+// keep the low w bits, sign-extended (a VHDL slice).  bfe.s32 with a register length is one SGXT.
+__device__ __forceinline__ int32_t sgxt32(int32_t v, int w)
 {
-    using U = typename LaneBits<T>::U;
-    const int sh = LaneBits<T>::bits - w;
-    return (T)((U)v << sh) >> sh;
+    int32_t r;
+    asm("bfe.s32 %0, %1, 0, %2;" : "=r"(r) : "r"(v), "r"(w));
+    return r;
+}
+template <typename T> __device__ __forceinline__ T wrapw(T v, int w);
+template <> __device__ __forceinline__ int32_t wrapw<int32_t>(int32_t v, int w) { return sgxt32(v, w); }
+template <> __device__ __forceinline__ int64_t wrapw<int64_t>(int64_t v, int w)
+{
+    if (w <= 32) return (int64_t)sgxt32((int32_t)v, w);          // w is uniform: no divergence
+    const int32_t hi = sgxt32((int32_t)(v >> 32), w - 32);
+    return (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)v);
 }
 
 __device__ __forceinline__ int64_t wrap48_64(int64_t v) { return (int64_t)((uint64_t)v << 16) >> 16; }

@@ -77,7 +77,13 @@ void build_passes(Plan &pl)
 
     struct Span { int lo_bit, bits; bool strided; };
     std::vector<Span> spans;
-    if (n <= 13) {
+    const bool f16 = g.use_fly && fast16_supported(g) && !std::getenv("INTFFT_DISABLE_FAST16");
+    if (f16 && n >= 13) {
+        // packed-16 kernels: top 4 or 8 bits as a strided pass, the rest (9..12 bits) contiguous
+        const int g_hi = n <= 16 ? 4 : 8, g_lo = n - g_hi;
+        if (!dit) { spans.push_back({g_lo, g_hi, true}); spans.push_back({0, g_lo, false}); }
+        else      { spans.push_back({0, g_lo, false}); spans.push_back({g_lo, g_hi, true}); }
+    } else if (n <= 13) {
         spans.push_back({0, n, false});
     } else {
         const int g_hi = (n - 12) < 4 ? 4 : (n - 12);
@@ -92,7 +98,7 @@ void build_passes(Plan &pl)
         PassDesc pd{};
         PassParams &kp = pd.kp;
         kp.n = n;
-        kp.L = (!sp.strided && n == 13) ? 13 : 12;
+        kp.L = (!f16 && !sp.strided && n == 13) ? 13 : 12;
         kp.g = sp.bits;
         kp.pb = sp.lo_bit;
         kp.c = sp.strided ? kp.L - sp.bits : 0;
@@ -113,7 +119,7 @@ void build_passes(Plan &pl)
         pd.threads = 1 << (kp.L - 4);
         pd.smem_bytes = ((size_t)1 << kp.L) * (pd.lane == LANE_I32_P64 ? 8 : 16);
         pd.scratch_in = pd.scratch_out = -1;
-        pd.fast16 = false;
+        pd.fast16 = f16 && n >= 8;
         stages_done += sp.bits;
         pl.passes.push_back(pd);
     }
@@ -128,8 +134,6 @@ void build_passes(Plan &pl)
             if (need > pl.scratch_bytes[0]) pl.scratch_bytes[0] = need;
         }
     }
-    if (pl.passes.size() == 1 && g.use_fly && fast16_supported(g) && !std::getenv("INTFFT_DISABLE_FAST16"))
-        pl.passes[0].fast16 = true;
 }
 
 int upload_twiddles(Plan &pl)
@@ -264,8 +268,9 @@ static int exec_frames(intfft_plan *p, const void *d_in, void *d_out, long long 
         pd.kp.tw = p->d_tw;
         pd.kp.total = total;
         pd.kp.n_tiles = pd.kp.c > 0 ? (frames << (n - pd.kp.L)) : ((total + (1ll << pd.kp.L) - 1) >> pd.kp.L);
-        const int e = pd.fast16 ? launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream)
-                                : launch_tile_pass(pd, p->mode, dit, p->num_sms, cuda_stream);
+        const int e = !pd.fast16 ? launch_tile_pass(pd, p->mode, dit, p->num_sms, cuda_stream)
+                      : (pd.kp.c > 0 ? launch_fast16_strided(pd, dit, p->d_twp, p->num_sms, cuda_stream)
+                                     : launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream));
         if (e) return INTFFT_ECUDA;
     }
     return INTFFT_OK;

@@ -89,7 +89,9 @@ __device__ __forceinline__ uint32_t pack(int re, int im) { return __byte_perm((u
 // -v for v >= 0, ~v for v < 0  (int_dif2_fly.vhd:299-303)
 __device__ __forceinline__ int negq(int v) { return (v >> 31) - v; }
 
-template <bool DIT, bool DW16>
+// RAWY (DIF, DW16 only): leave Y as the raw 32-bit sum of products; its value is raw >> 16, which the
+// packer takes straight from the upper half-words (PRMT 0x7632) instead of two shifts + PRMT.
+template <bool DIT, bool DW16, bool RAWY = false>
 __device__ __forceinline__ void fly(int s, bool odd, int &ar, int &ai, int &br, int &bi, int wr, int wi,
                                     int sh_full, int sh_half)
 {
@@ -108,8 +110,8 @@ __device__ __forceinline__ void fly(int s, bool odd, int &ar, int &ai, int &br, 
         } else {
             const int pr = (int)((unsigned)sr * (unsigned)wr - (unsigned)si * (unsigned)wi);
             const int pi = (int)((unsigned)sr * (unsigned)wi + (unsigned)si * (unsigned)wr);
-            br = DW16 ? sra<16>(pr) : (pr >> sh_full);
-            bi = DW16 ? sra<16>(pi) : (pi >> sh_full);
+            br = RAWY ? pr : (DW16 ? sra<16>(pr) : (pr >> sh_full));
+            bi = RAWY ? pi : (DW16 ? sra<16>(pi) : (pi >> sh_full));
         }
     } else {
         int hr, hi;                                             // BW >> 1
@@ -134,7 +136,7 @@ __device__ __forceinline__ void fly(int s, bool odd, int &ar, int &ai, int &br, 
 }
 
 // R stages (global bits LO .. LO+R-1) on the 16 register-resident samples
-template <int LO, int R, bool DIT, bool DW16, typename TW>
+template <int LO, int R, bool DIT, bool DW16, bool RAWLAST, typename TW>
 __device__ __forceinline__ void round_regs(int (&re)[16], int (&im)[16], const TW &tw, bool tid_odd, int sh_full,
                                            int sh_half)
 {
@@ -149,7 +151,10 @@ __device__ __forceinline__ void round_regs(int (&re)[16], int (&im)[16], const T
             const bool odd = (LO == 0) ? ((m & 1) != 0) : tid_odd;    // twiddle index bit 0 (STAGE = 1 only)
             int wr = 0, wi = 0;
             if (LO + q >= 2) tw(w, wr, wi);
-            fly<DIT, DW16>(LO + q, odd, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi, sh_full, sh_half);
+            if (RAWLAST && step == R - 1)
+                fly<DIT, DW16, true>(LO + q, odd, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi, sh_full, sh_half);
+            else
+                fly<DIT, DW16>(LO + q, odd, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi, sh_full, sh_half);
         }
     }
 }
@@ -294,10 +299,13 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
             }
 
             // ---- butterflies ----
-            if (r == 0) round_regs<0, R0, DIT, DW16>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
-            else if (r == 1 && MIDSM) round_regs<R0, 4, DIT, DW16>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
-            else if (r == 1) round_regs<R0, 4, DIT, DW16>(re, im, TwRegs{uwr[0], uwi[0]}, tid_odd, sh_full, sh_half);
-            else round_regs<R0 + 4, 4, DIT, DW16>(re, im, TwRegs{uwr[NR - 2], uwi[NR - 2]}, tid_odd, sh_full, sh_half);
+            // DIF upper rounds end with a multiply stage on register bit 0 (global bit >= 2): odd registers
+            // then hold raw products and are packed from their upper half-words
+            constexpr bool RAW = !DIT && DW16 && R0 >= 2;
+            if (r == 0) round_regs<0, R0, DIT, DW16, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
+            else if (r == 1 && MIDSM) round_regs<R0, 4, DIT, DW16, RAW>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
+            else if (r == 1) round_regs<R0, 4, DIT, DW16, RAW>(re, im, TwRegs{uwr[0], uwi[0]}, tid_odd, sh_full, sh_half);
+            else round_regs<R0 + 4, 4, DIT, DW16, RAW>(re, im, TwRegs{uwr[NR - 2], uwi[NR - 2]}, tid_odd, sh_full, sh_half);
 
             // ---- hand the samples on: to the exchange tile, or to HBM after the last round ----
             if (r == 0 && R0 == 4) {
@@ -316,7 +324,8 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
                     const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
-                    const uint32_t x = pack(re[m], im[m]);
+                    const uint32_t x = (RAW && r > 0 && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632)
+                                                                 : pack(re[m], im[m]);
                     if (last) { if (full || (g0 + base + off) < p.total) p.out[g0 + base + off] = x; }
                     else sm[pbase + phys(off)] = x;
                 }
@@ -331,6 +340,121 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strided pass for NFFT = 13..20 (16-bit scaled TRUNCATE): the top G = 4 or 8 stage bits of a frame.
+// A tile is 2^G rows (stride 2^(NFFT-G) samples) by 2^(12-G) contiguous columns; a CTA keeps one
+// column block ("mid") and walks over frames, so the between-pass twiddles — which depend on the
+// column, not on the frame — are hoisted once per work unit exactly like in the single-tile kernel.
+// The remaining NFFT-G bits are done by fast16_kernel<NFFT-G> on contiguous blocks (its twiddles
+// W_s[k], s < 12, are the same table entries for every NFFT).
+struct Strided16Params {
+    const uint32_t *in;
+    uint32_t *out;
+    const int2 *twp;
+    long long batch;
+    int n;                  // NFFT
+    int frames_per_unit;
+    long long n_units;      // mid_count * ceil(batch / frames_per_unit)
+    int dw, sh_full, sh_half;
+};
+
+template <int G, bool DIT, bool DW16>
+__global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_constant__ Strided16Params p)
+{
+    constexpr int C = 12 - G;                       // log2 contiguous columns per tile
+    constexpr int NR = G / 4;                       // rounds: local bits [8,12) and, for G = 8, [4,8)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);
+    uint32_t(*work)[kTileWords] = reinterpret_cast<uint32_t(*)[kTileWords]>(smem_raw + kSmemHead);
+
+    const unsigned tid = threadIdx.x;
+    const int sh_full = p.sh_full, sh_half = p.sh_half;
+    const int pb = p.n - G;                         // lowest global bit of this pass
+    const unsigned cmask = (1u << C) - 1u;
+    const int mid_bits = pb - C;
+    const long long row_stride = 1ll << pb;
+
+    int it = 0;
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const unsigned mid = (unsigned)(u & ((1ll << mid_bits) - 1));
+        const long long f0 = (u >> mid_bits) * p.frames_per_unit;
+        const long long f1 = (f0 + p.frames_per_unit < p.batch) ? f0 + p.frames_per_unit : p.batch;
+        // twiddle index of local position l (only its bits below the stage bit matter)
+        auto kidx = [&](unsigned l) { return ((l >> C) << pb) | (mid << C) | (l & cmask); };
+
+        // ---- twiddles of this column block ----
+        int uwr[15], uwi[15];                       // top round: local bits 8..11
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < (1 << q); ++j) {
+                const int sgl = pb + (8 + q - C);
+                const int2 w = __ldg(p.twp + (1u << sgl) + (kidx(tid | ((unsigned)j << 8)) & ((1u << sgl) - 1u)));
+                uwr[(1 << q) - 1 + j] = w.x;
+                uwi[(1 << q) - 1 + j] = w.y;
+            }
+        if (NR == 2) {                              // lower round: local bits 4..7, table[w][tid & 15]
+            __syncthreads();                        // previous unit's readers are done
+            if (tid < 240) {
+                const int w = tid >> 4, lo4 = tid & 15;
+                const int q = w >= 7 ? 3 : (w >= 3 ? 2 : (w >= 1 ? 1 : 0));
+                const int j = w - ((1 << q) - 1);
+                const int sgl = pb + (4 + q - C);
+                midtw[w * 16 + lo4] = __ldg(p.twp + (1u << sgl) + (kidx((unsigned)lo4 | ((unsigned)j << 4)) & ((1u << sgl) - 1u)));
+            }
+            __syncthreads();
+        }
+
+        for (long long f = f0; f < f1; ++f, ++it) {
+            uint32_t *sm = work[it & 1];
+            const long long gbase = (f << p.n) + ((long long)mid << C);
+            int re[16], im[16];
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) {
+                const int r = DIT ? rr : NR - 1 - rr;              // r = 0: local bits 12-4*NR.., r = NR-1: 8..11
+                const int lo = 12 - 4 * (NR - r);
+                const bool first = rr == 0, last = rr == NR - 1;
+                const unsigned base = (tid & ((1u << lo) - 1u)) | ((tid >> lo) << (lo + 4));
+                const unsigned pbase = phys(base);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned l = base | ((unsigned)m << lo);
+                    uint32_t x;
+                    if (first) x = __ldg(p.in + gbase + (long long)(l >> C) * row_stride + (l & cmask));
+                    else x = sm[pbase + phys((unsigned)m << lo)];
+                    unpack<DW16>(x, p.dw, re[m], im[m]);
+                }
+                constexpr bool RAW = !DIT && DW16;
+                if (lo == 8) round_regs<8, 4, DIT, DW16, RAW && (NR == 2)>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
+                else round_regs<4, 4, DIT, DW16, false>(re, im, TwSmem{midtw + (tid & 15u)}, false, sh_full, sh_half);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned l = base | ((unsigned)m << lo);
+                    if (last) {
+                        p.out[gbase + (long long)(l >> C) * row_stride + (l & cmask)] = pack(re[m], im[m]);
+                    } else {
+                        const uint32_t x = (RAW && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632)
+                                                            : pack(re[m], im[m]);
+                        sm[pbase + phys((unsigned)m << lo)] = x;
+                    }
+                }
+                if (!last) __syncthreads();
+            }
+        }
+    }
+}
+
+template <int G, bool DIT, bool DW16>
+cudaError_t launch_strided_k(const Strided16Params &p, int grid, cudaStream_t st)
+{
+    const int smem = kSmemHead + 2 * kTileWords * 4;
+    auto k = fast16_strided_kernel<G, DIT, DW16>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
 }
 
 template <int NLOG2, bool DIT, bool DW16>
@@ -357,7 +481,46 @@ cudaError_t launch_n(const Fast16Params &p, bool dit, bool dw16, int grid, cudaS
 bool fast16_supported(const intfft_generics &g)
 {
     return g.format == 0 && g.rndmode == 0 && g.use_fly == 1 && g.data_width <= 16 && g.twdl_width <= 16 &&
-           g.nfft_log2 >= 8 && g.nfft_log2 <= 12;
+           g.nfft_log2 >= 8 && g.nfft_log2 <= 20;
+}
+
+// top-bits pass of an NFFT >= 13 plan: kp.g in {4, 8}, kp.pb = NFFT - kp.g
+int launch_fast16_strided(const PassDesc &pd, bool dit, const int2 *twp, int num_sms, void *stream)
+{
+    Strided16Params p{};
+    p.in = reinterpret_cast<const uint32_t *>(pd.kp.in);
+    p.out = reinterpret_cast<uint32_t *>(pd.kp.out);
+    p.twp = twp;
+    p.n = pd.kp.n;
+    p.batch = pd.kp.total >> pd.kp.n;
+    p.dw = pd.kp.dw;
+    p.sh_full = 32 - p.dw;
+    p.sh_half = 33 - p.dw;
+    const int G = pd.kp.g, C = 12 - G, mid_bits = p.n - G - C;
+    const long long mids = 1ll << mid_bits;
+    long long grid = 3ll * num_sms;
+    // enough work units to balance the grid, few enough to amortise the per-unit twiddle loads
+    long long chunks = (8 * grid + mids - 1) / mids;
+    if (chunks < 1) chunks = 1;
+    if (chunks > p.batch) chunks = p.batch;
+    p.frames_per_unit = (int)((p.batch + chunks - 1) / chunks);
+    chunks = (p.batch + p.frames_per_unit - 1) / p.frames_per_unit;
+    p.n_units = mids * chunks;
+    if (grid > p.n_units) grid = p.n_units;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool dw16 = p.dw == 16;
+    cudaError_t e;
+    if (G == 4) {
+        if (!dit) e = dw16 ? launch_strided_k<4, false, true>(p, (int)grid, st) : launch_strided_k<4, false, false>(p, (int)grid, st);
+        else e = dw16 ? launch_strided_k<4, true, true>(p, (int)grid, st) : launch_strided_k<4, true, false>(p, (int)grid, st);
+    } else if (G == 8) {
+        if (!dit) e = dw16 ? launch_strided_k<8, false, true>(p, (int)grid, st) : launch_strided_k<8, false, false>(p, (int)grid, st);
+        else e = dw16 ? launch_strided_k<8, true, true>(p, (int)grid, st) : launch_strided_k<8, true, false>(p, (int)grid, st);
+    } else {
+        e = cudaErrorInvalidValue;
+    }
+    count_launch();
+    return (int)e;
 }
 
 int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
@@ -374,13 +537,13 @@ int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const
     p.sh_full = 32 - p.dw;
     p.sh_half = 33 - p.dw;
     for (int i = 0; i < 16; ++i) { p.lw_r[i] = lw_r[i]; p.lw_i[i] = lw_i[i]; }
-    long long grid = (pd.kp.n == 12 ? 3ll : 2ll) * num_sms;
+    long long grid = (pd.kp.g == 12 ? 3ll : 2ll) * num_sms;
     if (grid > p.n_tiles) grid = p.n_tiles;
     if (grid < 1) grid = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool dw16 = p.dw == 16;
     cudaError_t e;
-    switch (pd.kp.n) {
+    switch (pd.kp.g) {          // stage bits of this (contiguous) pass; == NFFT for single-pass plans
     case 8: e = launch_n<8>(p, dit, dw16, (int)grid, st); break;
     case 9: e = launch_n<9>(p, dit, dw16, (int)grid, st); break;
     case 10: e = launch_n<10>(p, dit, dw16, (int)grid, st); break;

@@ -82,6 +82,7 @@ int launch_tile_pass(const PassDesc &pd, int mode, bool dit, int num_sms, void *
 int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
                   int num_sms, void *stream);
 bool fast16_supported(const intfft_generics &g);
+int launch_fast16_strided(const PassDesc &pd, bool dit, const int2 *twp, int num_sms, void *stream);
 int launch_bypass(const void *in, void *out, long long n_scalars, int in_sb, int out_sb, int dw,
                   int zero_extend, void *stream);
 int launch_bitrev(int nfft_log2, int scalar_bytes, long long batch, const void *in, void *out, void *stream);

@@ -54,28 +54,38 @@ __device__ __forceinline__ void store_scalar_pair(void *base, long long idx, int
     }
 }
 
-// R stage bits of one round on the 16 register-resident samples of a thread.
+// Up to 4 stage bits of one round on the 16 register-resident samples of a thread.
 // Register index bit q (< R) is local tile bit lo + q; bits >= R enumerate independent groups.
-template <typename T, typename P, int MODE, bool DIT, int R>
-__device__ __forceinline__ void run_round(T (&re)[16], T (&im)[16], const PassParams &p, int lo,
+// One code body serves R = 1..4: steps for q >= R are skipped by a grid-uniform branch.
+// The twiddles of a step are fetched (read-only path) before its butterflies so the loads overlap.
+template <typename T, typename P, int MODE, bool DIT>
+__device__ __forceinline__ void run_round(T (&re)[16], T (&im)[16], const PassParams &p, int lo, int R,
                                           unsigned gbase, const unsigned (&goff)[16])
 {
 #pragma unroll
-    for (int step = 0; step < R; ++step) {
-        const int q = DIT ? step : R - 1 - step;
+    for (int step = 0; step < 4; ++step) {
+        const int q = DIT ? step : 3 - step;
+        if (q >= R) continue;
         const int s = p.pb + (lo + q - p.c);          // global bit == butterfly STAGE
         const StageInfo si = stage_info<DIT>(p, s);
         const unsigned kmask = (1u << s) - 1u;
         const unsigned kb = gbase & kmask;
         const int2 *tw = p.tw + (1u << s);
+        int2 w[8];
+        unsigned kk[8];
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
+        for (int m = 0, j = 0; m < 16; ++m) {
+            if (m & (1 << q)) continue;
+            kk[j] = kb | (goff[m] & kmask);
+            w[j] = (s >= 2) ? __ldg(tw + kk[j]) : make_int2(0, 0);
+            ++j;
+        }
+#pragma unroll
+        for (int m = 0, j = 0; m < 16; ++m) {
             if (m & (1 << q)) continue;
             const int mb = m | (1 << q);
-            const unsigned k = kb | (goff[m] & kmask);
-            int2 w = make_int2(0, 0);
-            if (s >= 2) w = __ldg(tw + k);
-            butterfly<T, P, MODE, DIT>(re[m], im[m], re[mb], im[mb], si, p.cm, k, w);
+            butterfly<T, P, MODE, DIT>(re[m], im[m], re[mb], im[mb], si, p.cm, kk[j], w[j]);
+            ++j;
         }
     }
 }
@@ -138,12 +148,7 @@ __global__ void __launch_bounds__(512) tile_kernel(const __grid_constant__ PassP
                 const E v = tile[pbase ^ poff[m]];
                 re[m] = v.x; im[m] = v.y;
             }
-            switch (R) {
-            case 4: run_round<T, P, MODE, DIT, 4>(re, im, p, lo, gbase, goff); break;
-            case 3: run_round<T, P, MODE, DIT, 3>(re, im, p, lo, gbase, goff); break;
-            case 2: run_round<T, P, MODE, DIT, 2>(re, im, p, lo, gbase, goff); break;
-            default: run_round<T, P, MODE, DIT, 1>(re, im, p, lo, gbase, goff); break;
-            }
+            run_round<T, P, MODE, DIT>(re, im, p, lo, R, gbase, goff);
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
                 E v; v.x = re[m]; v.y = im[m];

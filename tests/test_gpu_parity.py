@@ -113,10 +113,22 @@ def test_parity_multipass(ib, oracle, nfft, dw, fmt, direction):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("nfft", [13, 14, 15, 16, 17, 18, 19])
+@pytest.mark.parametrize("direction", [0, 1])
+def test_parity_packed16_two_pass(ib, oracle, nfft, direction):
+    """NFFT 13..19, 16-bit scaled: strided packed-16 pass (top 4 / 8 bits) + contiguous packed-16 pass."""
+    for dw, tw, batch in ((16, 16, 3), (12, 14, 2)):
+        got, want = _run_both(ib, oracle, batch, seed=nfft * 3 + direction, via="device", NFFT=nfft, DATA_WIDTH=dw,
+                              TWDL_WIDTH=tw, FORMAT=0, RNDMODE=0, direction=direction)
+        assert np.array_equal(got, want), (dw, tw)
+
+
 @pytest.mark.parametrize("xser", ["NEW", "OLD"])
 def test_parity_nfft20_taylor_extension(ib, oracle, xser):
     """BASELINE config c4 shape (one frame): 2^20 points, Taylor twiddles on STAGE 11..19."""
     got, want = _run_both(ib, oracle, 1, seed=20, via="device", NFFT=20, DATA_WIDTH=16, FORMAT=0, XSER=xser)
+    assert np.array_equal(got, want)
+    got, want = _run_both(ib, oracle, 2, seed=21, via="device", NFFT=20, DATA_WIDTH=16, FORMAT=0, XSER=xser, direction=1)
     assert np.array_equal(got, want)
 
 
