@@ -42,8 +42,11 @@ template <typename T> __device__ __forceinline__ T negq(T v, int w)
     return wrapw<T>(v >= 0 ? (T)(0 - v) : (T)~v, w);
 }
 
+// `ow` = output width.  Only the ROUNDING difference can leave it: A - B = 2^DTW - 1 rounds up to
+// 2^(DTW-1), which the reference keeps in DTW bits (rnd(DTW downto 1) + '1', int_dif2_fly.vhd:201-216),
+// i.e. it wraps to -2^(DTW-1).
 template <int MODE, typename T>
-__device__ __forceinline__ void addsub(T a, T b, T &ad, T &su)
+__device__ __forceinline__ void addsub(T a, T b, int ow, T &ad, T &su)
 {
     using U = typename LaneBits<T>::U;
     if (MODE == MODE_TRUNC) {          // inputs sliced (DTW-1 downto 1)
@@ -53,7 +56,7 @@ __device__ __forceinline__ void addsub(T a, T b, T &ad, T &su)
     } else if (MODE == MODE_ROUND) {   // (v >> 1) + v(0) on the exact sum / difference
         const T s = (T)((U)a + (U)b), d = (T)((U)a - (U)b);
         ad = (s >> 1) + (s & 1);
-        su = (d >> 1) + (d & 1);
+        su = wrapw<T>((d >> 1) + (d & 1), ow);
     } else {                           // exact, one bit of growth
         ad = (T)((U)a + (U)b);
         su = (T)((U)a - (U)b);
@@ -112,8 +115,8 @@ __device__ __forceinline__ void butterfly(T &a_re, T &a_im, T &b_re, T &b_im, co
 {
     if (!DIT) {
         T ad_re, ad_im, su_re, su_im;
-        addsub<MODE, T>(a_re, b_re, ad_re, su_re);
-        addsub<MODE, T>(a_im, b_im, ad_im, su_im);
+        addsub<MODE, T>(a_re, b_re, si.ow, ad_re, su_re);
+        addsub<MODE, T>(a_im, b_im, si.ow, ad_im, su_im);
         a_re = ad_re;
         a_im = ad_im;
         if (si.s == 0) {
@@ -142,8 +145,8 @@ __device__ __forceinline__ void butterfly(T &a_re, T &a_im, T &b_re, T &b_im, co
             bw_re = o_im;
         }
         T x_re, x_im, y_re, y_im;
-        addsub<MODE, T>(a_re, bw_re, x_re, y_re);
-        addsub<MODE, T>(a_im, bw_im, x_im, y_im);
+        addsub<MODE, T>(a_re, bw_re, si.ow, x_re, y_re);
+        addsub<MODE, T>(a_im, bw_im, si.ow, x_im, y_im);
         a_re = x_re; a_im = x_im;
         b_re = y_re; b_im = y_im;
     }

@@ -77,8 +77,10 @@ void build_passes(Plan &pl)
 
     struct Span { int lo_bit, bits; bool strided; };
     std::vector<Span> spans;
-    const bool f16 = g.use_fly && fast16_supported(g) && !std::getenv("INTFFT_DISABLE_FAST16");
-    if (f16 && n >= 13) {
+    const bool no_fast = std::getenv("INTFFT_DISABLE_FAST16") != nullptr;   // tests: force the generic kernel
+    const bool f16 = !no_fast && g.use_fly && fast16_supported(g);
+    const bool f32 = !no_fast && !f16 && fast32_supported(g);
+    if ((f16 || f32) && n >= 13) {
         // packed-16 kernels: top 4 or 8 bits as a strided pass, the rest (9..12 bits) contiguous
         const int g_hi = n <= 16 ? 4 : 8, g_lo = n - g_hi;
         if (!dit) { spans.push_back({g_lo, g_hi, true}); spans.push_back({0, g_lo, false}); }
@@ -98,7 +100,7 @@ void build_passes(Plan &pl)
         PassDesc pd{};
         PassParams &kp = pd.kp;
         kp.n = n;
-        kp.L = (!f16 && !sp.strided && n == 13) ? 13 : 12;
+        kp.L = (!f16 && !f32 && !sp.strided && n == 13) ? 13 : 12;
         kp.g = sp.bits;
         kp.pb = sp.lo_bit;
         kp.c = sp.strided ? kp.L - sp.bits : 0;
@@ -119,7 +121,7 @@ void build_passes(Plan &pl)
         pd.threads = 1 << (kp.L - 4);
         pd.smem_bytes = ((size_t)1 << kp.L) * (pd.lane == LANE_I32_P64 ? 8 : 16);
         pd.scratch_in = pd.scratch_out = -1;
-        pd.fast16 = f16 && n >= 8;
+        pd.path = f16 ? 1 : (f32 ? 2 : 0);
         stages_done += sp.bits;
         pl.passes.push_back(pd);
     }
@@ -148,7 +150,12 @@ int upload_twiddles(Plan &pl)
     }
     if (cudaMalloc(&pl.d_tw, cnt * sizeof(int2)) != cudaSuccess) return INTFFT_ENOMEM;
     if (cudaMemcpy(pl.d_tw, tab.data(), cnt * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) return INTFFT_ECUDA;
-    if (!pl.passes.empty() && pl.passes[0].fast16) {
+    for (int s = 2; s <= 3 && s < n; ++s)
+        for (int k = 0; k < (1 << s); ++k) {
+            pl.lw32_r[(1 << s) - 1 + k] = tab[((size_t)1 << s) + k].x;
+            pl.lw32_i[(1 << s) - 1 + k] = tab[((size_t)1 << s) + k].y;
+        }
+    if (!pl.passes.empty() && pl.passes[0].path == 1) {
         // 32-bit-product kernel: W << e with e = 33 - TWDL_WIDTH - DATA_WIDTH puts the multiplier's
         // output slice P(DTW+TWD-2 downto TWD-1) (int_cmult_dsp48.vhd:189-190) at bits 31 .. 32-DTW
         const int e = 33 - pl.g.twdl_width - pl.g.data_width;
@@ -268,9 +275,14 @@ static int exec_frames(intfft_plan *p, const void *d_in, void *d_out, long long 
         pd.kp.tw = p->d_tw;
         pd.kp.total = total;
         pd.kp.n_tiles = pd.kp.c > 0 ? (frames << (n - pd.kp.L)) : ((total + (1ll << pd.kp.L) - 1) >> pd.kp.L);
-        const int e = !pd.fast16 ? launch_tile_pass(pd, p->mode, dit, p->num_sms, cuda_stream)
-                      : (pd.kp.c > 0 ? launch_fast16_strided(pd, dit, p->d_twp, p->num_sms, cuda_stream)
-                                     : launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream));
+        int e;
+        if (pd.path == 1)
+            e = pd.kp.c > 0 ? launch_fast16_strided(pd, dit, p->d_twp, p->num_sms, cuda_stream)
+                            : launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream);
+        else if (pd.path == 2)
+            e = launch_fast32(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
+        else
+            e = launch_tile_pass(pd, p->mode, dit, p->num_sms, cuda_stream);
         if (e) return INTFFT_ECUDA;
     }
     return INTFFT_OK;

@@ -1,0 +1,491 @@
+// Specialised stage-chain kernels for every plan whose values fit 32-bit lanes (all three output
+// modes, both directions, TWDL_WIDTH 8..27, single- and double-DSP multiplier arrangements):
+// BASELINE c5 (8192-pt 18-bit DIT), ROUNDING / UNSCALED 16-bit plans, 17..27-bit scaled plans.
+//
+// Same structure as the packed-16 kernels (intfft_fast16.cu): 4096-sample tiles, 256 threads,
+// 16 samples per thread for 4 consecutive stages, twiddles hoisted (registers for the top round, a
+// small shared table for the middle round, kernel parameters for the lowest round), one CTA barrier
+// per tile.  Differences: samples are {re:int32, im:int32} in shared memory (no pack / unpack),
+// products are 64-bit (IMAD.WIDE + funnel shift + SGXT), the multiplier arrangement of a stage is a
+// grid-uniform run-time choice, and NFFT >= 13 is a strided top pass + a contiguous pass.
+//
+// Reference rules implemented: int_dif2_fly.vhd:142-373, int_dit2_fly.vhd:140-325,
+// int_cmult_dsp48.vhd:182-190 / 307-317 (single), int_cmult_dbl18_dsp48.vhd:163-181 and
+// int_cmult_dbl35_dsp48.vhd:155-168 (double; its 48-bit wrap cannot reach the kept bits when the
+// result is <= 32 bits wide, so it is not materialised here).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "intfft_arith.cuh"
+
+namespace intfft {
+
+namespace f32 {
+
+struct Fast32Params {
+    const void *in;
+    void *out;
+    const int2 *tw;          // raw twiddles, entry (1 << s) + k
+    long long n_tiles;       // contiguous: tiles of 4096 samples
+    long long total;         // frames * N
+    long long batch;
+    int n;                   // NFFT of the whole transform
+    int dw, format;
+    int in_sb, out_sb;       // scalar bytes of the containers read / written: 2 or 4
+    int in_wrap;
+    int frames_per_unit;     // strided pass only
+    long long n_units;       // strided pass only
+    CmultConsts cm;
+    int lw_r[16], lw_i[16];  // lowest-round twiddles, index (1 << s) - 1 + k, s = 2, 3
+};
+
+// element (8-byte) index inside a 4096-sample tile -> slot in the padded exchange tile; additive for
+// disjoint bit sets, conflict-free for LDS.64 at stride 256 / 16 and for LDS.128 on 16 contiguous samples
+__host__ __device__ constexpr unsigned phys8(unsigned i) { return i + 2u * (i >> 4); }
+constexpr unsigned kTile8 = 4608;
+constexpr unsigned kHead32 = 128 + 15 * 16 * 8;
+
+// one scalar of a sample: the value and (TRUNCATE only; dead code elsewhere) its floor-half, which is
+// all a TRUNCATE butterfly ever reads (inputs sliced (DTW-1 downto 1), int_dif2_fly.vhd:150-153)
+struct V {
+    int f, h;
+};
+__device__ __forceinline__ V mk(int f) { return V{f, f >> 1}; }
+
+// multiplier arrangement policy of a kernel instance: every stage single-DSP, or chosen per stage
+enum { KIND_SINGLE = 0, KIND_MIXED = 1 };
+
+struct Stg {
+    int s, ow, dtwc, kind;
+};
+template <bool DIT, int MODE, int KIND>
+__device__ __forceinline__ Stg stage_of(const Fast32Params &p, int s)
+{
+    constexpr int FORMAT = MODE == MODE_UNSCALED ? 1 : 0;
+    Stg st;
+    st.s = s;
+    const int ii = DIT ? s : p.n - 1 - s;
+    const int dtw = p.dw + ii * FORMAT;
+    st.ow = dtw + FORMAT;
+    st.dtwc = DIT ? dtw : st.ow;
+    st.kind = (KIND == KIND_SINGLE) ? 0 : (st.dtwc < p.cm.lim_single ? 0 : 1);
+    return st;
+}
+
+__device__ __forceinline__ int negq32(int v) { return (v >> 31) - v; }
+
+// double-DSP arrangement (rare: only stages whose operand is >= 28 / 26 / 19 bits wide); kept out of
+// line so the common single-DSP path stays branch-free and small
+// bits [sh+w-1 : sh] of a 64-bit value, sign-extended: funnel-left by 64-sh-w (high word), then an
+// arithmetic right shift by 32-w  (bfe.s32 with a register length costs three instructions instead)
+__device__ __forceinline__ int field(long long t, int sh, int w)
+{
+    const int hi = (int)(((unsigned long long)t << (64 - sh - w)) >> 32);
+    return hi >> (32 - w);
+}
+// low w bits of a 32-bit value, sign-extended
+__device__ __forceinline__ int sx(int v, int w) { return (int)((unsigned)v << (32 - w)) >> (32 - w); }
+
+template <int MODE>
+__device__ __noinline__ void cmul32_dbl(int dr, int di, int wr, int wi, int k_pre, int sh_post, int dtwc, int (&o)[4])
+{
+    const long long tr = (((long long)dr * wr) >> k_pre) - (((long long)di * wi) >> k_pre);
+    const long long ti = (((long long)dr * wi) >> k_pre) + (((long long)di * wr) >> k_pre);
+    o[0] = field(tr, sh_post, dtwc);
+    o[1] = field(ti, sh_post, dtwc);
+    o[2] = MODE == MODE_TRUNC ? field(tr, sh_post + 1, dtwc - 1) : 0;
+    o[3] = MODE == MODE_TRUNC ? field(ti, sh_post + 1, dtwc - 1) : 0;
+}
+
+template <int MODE, int KIND>
+__device__ __forceinline__ void cmul32(int dr, int di, int wr, int wi, const CmultConsts &cm, const Stg &st,
+                                       V &o_re, V &o_im)
+{
+    if (KIND == KIND_MIXED && st.kind != 0) {
+        int o[4];
+        cmul32_dbl<MODE>(dr, di, wr, wi, cm.k_pre, cm.sh_post, st.dtwc, o);
+        o_re = V{o[0], o[2]};
+        o_im = V{o[1], o[3]};
+        return;
+    }
+    const long long tr = (long long)dr * wr - (long long)di * wi;      // 2 x IMAD.WIDE
+    const long long ti = (long long)dr * wi + (long long)di * wr;
+    const int sh = cm.sh_single;
+    o_re.f = field(tr, sh, st.dtwc);
+    o_im.f = field(ti, sh, st.dtwc);
+    if (MODE == MODE_TRUNC) {
+        o_re.h = field(tr, sh + 1, st.dtwc - 1);
+        o_im.h = field(ti, sh + 1, st.dtwc - 1);
+    } else {
+        o_re.h = o_im.h = 0;
+    }
+}
+
+template <int MODE> __device__ __forceinline__ void addsub32(const V &a, const V &b, int ow, V &x, V &y)
+{
+    int xf, yf;
+    if (MODE == MODE_TRUNC) {
+        xf = a.h + b.h;
+        yf = a.h - b.h;
+    } else if (MODE == MODE_ROUND) {            // (v >> 1) + v(0) == (v + 1) >> 1
+        xf = (int)((unsigned)a.f + (unsigned)b.f + 1u) >> 1;
+        // the rounded difference can reach 2^(ow-1) and is kept in ow bits by the reference
+        yf = sx((int)((unsigned)a.f - (unsigned)b.f + 1u) >> 1, ow);
+    } else {
+        xf = (int)((unsigned)a.f + (unsigned)b.f);
+        yf = (int)((unsigned)a.f - (unsigned)b.f);
+    }
+    x = mk(xf);
+    y = mk(yf);
+}
+
+template <bool DIT, int MODE, int KIND>
+__device__ __forceinline__ void fly32(const Stg &st, bool odd, const CmultConsts &cm, V &ar, V &ai, V &br, V &bi,
+                                      int wr, int wi)
+{
+    if (!DIT) {
+        V xr, xi, sr, si;
+        addsub32<MODE>(ar, br, st.ow, xr, sr);
+        addsub32<MODE>(ai, bi, st.ow, xi, si);
+        ar = xr;
+        ai = xi;
+        if (st.s == 0) {
+            br = sr;
+            bi = si;
+        } else if (st.s == 1) {
+            br = odd ? si : sr;
+            bi = odd ? mk(negq32(sr.f)) : si;
+        } else {
+            cmul32<MODE, KIND>(sr.f, si.f, wr, wi, cm, st, br, bi);
+        }
+    } else {
+        V wr_, wi_;                                   // BW
+        if (st.s == 0) {
+            wr_ = br;
+            wi_ = bi;
+        } else if (st.s == 1) {
+            wr_ = odd ? mk(negq32(bi.f)) : br;
+            wi_ = odd ? br : bi;
+        } else {                                      // DI_RE <= IB_IM, DI_IM <= IB_RE; DO_RE => bw_im, DO_IM => bw_re
+            V o_re, o_im;
+            cmul32<MODE, KIND>(bi.f, br.f, wr, wi, cm, st, o_re, o_im);
+            wi_ = o_re;
+            wr_ = o_im;
+        }
+        V xr, xi, yr, yi;
+        addsub32<MODE>(ar, wr_, st.ow, xr, yr);
+        addsub32<MODE>(ai, wi_, st.ow, xi, yi);
+        ar = xr; ai = xi;
+        br = yr; bi = yi;
+    }
+}
+
+struct TwRegs32 {
+    const int (&r)[15];
+    const int (&i)[15];
+    __device__ __forceinline__ void operator()(int w, int &wr, int &wi) const { wr = r[w]; wi = i[w]; }
+};
+struct TwSmem32 {
+    const int2 *t;
+    int pitch;
+    __device__ __forceinline__ void operator()(int w, int &wr, int &wi) const
+    {
+        const int2 v = t[w * pitch];
+        wr = v.x;
+        wi = v.y;
+    }
+};
+
+// R stages on register bits 0..R-1 (global stage numbers S0 .. S0+R-1) of the 16 resident samples
+template <int R, bool DIT, int MODE, int KIND, typename TW>
+__device__ __forceinline__ void round32(V (&re)[16], V (&im)[16], const Fast32Params &p, int s0, const TW &tw,
+                                        bool lo_is_zero, bool tid_odd)
+{
+#pragma unroll
+    for (int step = 0; step < R; ++step) {
+        const int q = DIT ? step : R - 1 - step;
+        const Stg st = stage_of<DIT, MODE, KIND>(p, s0 + q);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            if (m & (1 << q)) continue;
+            const int w = (1 << q) - 1 + (m & ((1 << q) - 1));
+            int wr = 0, wi = 0;
+            if (st.s >= 2) tw(w, wr, wi);
+            const bool odd = lo_is_zero ? ((m & 1) != 0) : tid_odd;
+            fly32<DIT, MODE, KIND>(st, odd, p.cm, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi);
+        }
+    }
+}
+
+__device__ __forceinline__ void ld_sample(const void *base, long long idx, int sb, int &re, int &im)
+{
+    if (sb == 2) {
+        const unsigned x = __ldg(reinterpret_cast<const unsigned *>(base) + idx);
+        re = (int)(short)(x & 0xffffu);
+        im = (int)x >> 16;
+    } else {
+        const int2 v = __ldg(reinterpret_cast<const int2 *>(base) + idx);
+        re = v.x;
+        im = v.y;
+    }
+}
+__device__ __forceinline__ void st_sample(void *base, long long idx, int sb, int re, int im)
+{
+    if (sb == 2) reinterpret_cast<unsigned *>(base)[idx] = __byte_perm((unsigned)re, (unsigned)im, 0x5410);
+    else reinterpret_cast<int2 *>(base)[idx] = make_int2(re, im);
+}
+
+// ------------------------------------------------------------------------------------------------
+// contiguous pass: stage bits 0 .. NLOG2-1 of an NFFT = p.n transform (NLOG2 == p.n for one-pass plans)
+template <int NLOG2, bool DIT, int MODE, int KIND>
+__global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ Fast32Params p)
+{
+    constexpr int R0 = ((NLOG2 - 1) % 4) + 1;
+    constexpr int NR = 1 + (NLOG2 - R0) / 4;
+    static_assert(NR >= 2 && NR <= 3, "supported: 2^5 .. 2^12 points per tile");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);                  // [15][1 << R0]
+    int2(*work)[kTile8] = reinterpret_cast<int2(*)[kTile8]>(smem_raw + kHead32);
+
+    const unsigned tid = threadIdx.x;
+    const bool tid_odd = tid & 1u;
+
+    // ---- batch-invariant twiddles: round 1 -> shared table, round 2 -> registers ----
+    for (unsigned e = tid; e < 15u << R0; e += 256) {
+        const int w = e >> R0, low = e & ((1u << R0) - 1u);
+        const int q = w >= 7 ? 3 : (w >= 3 ? 2 : (w >= 1 ? 1 : 0));
+        const int j = w - ((1 << q) - 1);
+        midtw[e] = __ldg(p.tw + (1u << (R0 + q)) + low + ((unsigned)j << R0));
+    }
+    int uwr[15], uwi[15];
+    if (NR == 3) {
+        const int lo = R0 + 4;
+        const unsigned low = tid & ((1u << lo) - 1u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < (1 << q); ++j) {
+                const int2 w = __ldg(p.tw + (1u << (lo + q)) + low + ((unsigned)j << lo));
+                uwr[(1 << q) - 1 + j] = w.x;
+                uwi[(1 << q) - 1 + j] = w.y;
+            }
+    }
+    int lwr[15], lwi[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) { lwr[i] = p.lw_r[i]; lwi[i] = p.lw_i[i]; }
+    __syncthreads();
+
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        int2 *sm = work[it & 1];
+        const long long g0 = tile << 12;
+        const bool full = g0 + 4096 <= p.total;
+        V re[16], im[16];
+#pragma unroll
+        for (int rr = 0; rr < NR; ++rr) {
+            const int r = DIT ? rr : NR - 1 - rr;
+            const int lo = r == 0 ? 0 : R0 + 4 * (r - 1);
+            const int R = r == 0 ? R0 : 4;
+            const bool first = rr == 0, last = rr == NR - 1;
+            const unsigned base = (tid & ((1u << lo) - 1u)) | ((tid >> lo) << (lo + R));
+            const unsigned pbase = phys8(base);
+
+            if (first && full) {                      // whole tile inside the batch: no per-sample guards
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
+                    int a, b;
+                    ld_sample(p.in, g0 + base + off, p.in_sb, a, b);
+                    if (p.in_wrap) { a = sx(a, p.dw); b = sx(b, p.dw); }
+                    re[m] = mk(a);
+                    im[m] = mk(b);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
+                    int a = 0, b = 0;
+                    if (first) {
+                        if ((g0 + base + off) < p.total) {
+                            ld_sample(p.in, g0 + base + off, p.in_sb, a, b);
+                            if (p.in_wrap) { a = sx(a, p.dw); b = sx(b, p.dw); }
+                        }
+                    } else {
+                        const int2 v = sm[pbase + phys8(off)];
+                        a = v.x;
+                        b = v.y;
+                    }
+                    re[m] = mk(a);
+                    im[m] = mk(b);
+                }
+            }
+
+            if (r == 0) round32<R0, DIT, MODE, KIND>(re, im, p, 0, TwRegs32{lwr, lwi}, true, tid_odd);
+            else if (r == 1) round32<4, DIT, MODE, KIND>(re, im, p, R0, TwSmem32{midtw + (tid & ((1u << R0) - 1u)), 1 << R0}, false, tid_odd);
+            else round32<4, DIT, MODE, KIND>(re, im, p, R0 + 4, TwRegs32{uwr, uwi}, false, tid_odd);
+
+            if (last && full) {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
+                    st_sample(p.out, g0 + base + off, p.out_sb, re[m].f, im[m].f);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
+                    if (last) {
+                        if ((g0 + base + off) < p.total) st_sample(p.out, g0 + base + off, p.out_sb, re[m].f, im[m].f);
+                    } else {
+                        sm[pbase + phys8(off)] = make_int2(re[m].f, im[m].f);
+                    }
+                }
+            }
+            if (!last) {
+                const bool warp_local = (NR == 3 && R0 == 4) && ((DIT && rr == 0) || (!DIT && rr == 1));
+                if (warp_local) __syncwarp();
+                else __syncthreads();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// strided pass: the top G = 4 or 8 stage bits of an NFFT = 13..20 transform (see intfft_fast16.cu)
+template <int G, bool DIT, int MODE, int KIND>
+__global__ void __launch_bounds__(256, 2) fast32_strided_kernel(const __grid_constant__ Fast32Params p)
+{
+    constexpr int C = 12 - G;
+    constexpr int NR = G / 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);
+    int2(*work)[kTile8] = reinterpret_cast<int2(*)[kTile8]>(smem_raw + kHead32);
+
+    const unsigned tid = threadIdx.x;
+    const int pb = p.n - G;
+    const unsigned cmask = (1u << C) - 1u;
+    const int mid_bits = pb - C;
+    const long long row_stride = 1ll << pb;
+
+    int it = 0;
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const unsigned mid = (unsigned)(u & ((1ll << mid_bits) - 1));
+        const long long f0 = (u >> mid_bits) * p.frames_per_unit;
+        const long long f1 = (f0 + p.frames_per_unit < p.batch) ? f0 + p.frames_per_unit : p.batch;
+        auto kidx = [&](unsigned l) { return ((l >> C) << pb) | (mid << C) | (l & cmask); };
+
+        int uwr[15], uwi[15];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < (1 << q); ++j) {
+                const int sgl = pb + (8 + q - C);
+                const int2 w = __ldg(p.tw + (1u << sgl) + (kidx(tid | ((unsigned)j << 8)) & ((1u << sgl) - 1u)));
+                uwr[(1 << q) - 1 + j] = w.x;
+                uwi[(1 << q) - 1 + j] = w.y;
+            }
+        if (NR == 2) {
+            __syncthreads();
+            if (tid < 240) {
+                const int w = tid >> 4, lo4 = tid & 15;
+                const int q = w >= 7 ? 3 : (w >= 3 ? 2 : (w >= 1 ? 1 : 0));
+                const int j = w - ((1 << q) - 1);
+                const int sgl = pb + (4 + q - C);
+                midtw[w * 16 + lo4] = __ldg(p.tw + (1u << sgl) + (kidx((unsigned)lo4 | ((unsigned)j << 4)) & ((1u << sgl) - 1u)));
+            }
+            __syncthreads();
+        }
+
+        for (long long f = f0; f < f1; ++f, ++it) {
+            int2 *sm = work[it & 1];
+            const long long gbase = (f << p.n) + ((long long)mid << C);
+            V re[16], im[16];
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) {
+                const int r = DIT ? rr : NR - 1 - rr;
+                const int lo = 12 - 4 * (NR - r);
+                const bool first = rr == 0, last = rr == NR - 1;
+                const unsigned base = (tid & ((1u << lo) - 1u)) | ((tid >> lo) << (lo + 4));
+                const unsigned pbase = phys8(base);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned l = base | ((unsigned)m << lo);
+                    int a, b;
+                    if (first) {
+                        ld_sample(p.in, gbase + (long long)(l >> C) * row_stride + (l & cmask), p.in_sb, a, b);
+                        if (p.in_wrap) { a = sx(a, p.dw); b = sx(b, p.dw); }
+                    } else {
+                        const int2 v = sm[pbase + phys8((unsigned)m << lo)];
+                        a = v.x;
+                        b = v.y;
+                    }
+                    re[m] = mk(a);
+                    im[m] = mk(b);
+                }
+                if (lo == 8) round32<4, DIT, MODE, KIND>(re, im, p, pb + 8 - C, TwRegs32{uwr, uwi}, false, false);
+                else round32<4, DIT, MODE, KIND>(re, im, p, pb + 4 - C, TwSmem32{midtw + (tid & 15u), 16}, false, false);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned l = base | ((unsigned)m << lo);
+                    if (last) st_sample(p.out, gbase + (long long)(l >> C) * row_stride + (l & cmask), p.out_sb, re[m].f, im[m].f);
+                    else sm[pbase + phys8((unsigned)m << lo)] = make_int2(re[m].f, im[m].f);
+                }
+                if (!last) __syncthreads();
+            }
+        }
+    }
+}
+
+
+template <typename K> cudaError_t launch_any(K k, const Fast32Params &p, int grid, cudaStream_t st)
+{
+    const int smem = kHead32 + 2 * kTile8 * 8;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// one translation unit per direction keeps the build parallel
+template <int NLOG2, bool DIT> cudaError_t launch_contig(const Fast32Params &p, int mode, int kind, int grid, cudaStream_t st)
+{
+    switch (mode * 2 + kind) {
+    case MODE_TRUNC * 2 + 0: return launch_any(fast32_kernel<NLOG2, DIT, MODE_TRUNC, KIND_SINGLE>, p, grid, st);
+    case MODE_TRUNC * 2 + 1: return launch_any(fast32_kernel<NLOG2, DIT, MODE_TRUNC, KIND_MIXED>, p, grid, st);
+    case MODE_ROUND * 2 + 0: return launch_any(fast32_kernel<NLOG2, DIT, MODE_ROUND, KIND_SINGLE>, p, grid, st);
+    case MODE_ROUND * 2 + 1: return launch_any(fast32_kernel<NLOG2, DIT, MODE_ROUND, KIND_MIXED>, p, grid, st);
+    case MODE_UNSCALED * 2 + 0: return launch_any(fast32_kernel<NLOG2, DIT, MODE_UNSCALED, KIND_SINGLE>, p, grid, st);
+    default: return launch_any(fast32_kernel<NLOG2, DIT, MODE_UNSCALED, KIND_MIXED>, p, grid, st);
+    }
+}
+template <bool DIT> cudaError_t launch_contig_n(const Fast32Params &p, int bits, int mode, int kind, int grid, cudaStream_t st)
+{
+    switch (bits) {
+    case 8: return launch_contig<8, DIT>(p, mode, kind, grid, st);
+    case 9: return launch_contig<9, DIT>(p, mode, kind, grid, st);
+    case 10: return launch_contig<10, DIT>(p, mode, kind, grid, st);
+    case 11: return launch_contig<11, DIT>(p, mode, kind, grid, st);
+    case 12: return launch_contig<12, DIT>(p, mode, kind, grid, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+template <int G, bool DIT> cudaError_t launch_strided(const Fast32Params &p, int mode, int kind, int grid, cudaStream_t st)
+{
+    switch (mode * 2 + kind) {
+    case MODE_TRUNC * 2 + 0: return launch_any(fast32_strided_kernel<G, DIT, MODE_TRUNC, KIND_SINGLE>, p, grid, st);
+    case MODE_TRUNC * 2 + 1: return launch_any(fast32_strided_kernel<G, DIT, MODE_TRUNC, KIND_MIXED>, p, grid, st);
+    case MODE_ROUND * 2 + 0: return launch_any(fast32_strided_kernel<G, DIT, MODE_ROUND, KIND_SINGLE>, p, grid, st);
+    case MODE_ROUND * 2 + 1: return launch_any(fast32_strided_kernel<G, DIT, MODE_ROUND, KIND_MIXED>, p, grid, st);
+    case MODE_UNSCALED * 2 + 0: return launch_any(fast32_strided_kernel<G, DIT, MODE_UNSCALED, KIND_SINGLE>, p, grid, st);
+    default: return launch_any(fast32_strided_kernel<G, DIT, MODE_UNSCALED, KIND_MIXED>, p, grid, st);
+    }
+}
+
+}  // namespace f32
+
+// implemented in intfft_fast32_dif.cu / _dit.cu / _strided.cu
+int f32_launch_contig_dif(const f32::Fast32Params &p, int bits, int mode, int kind, int grid, void *stream);
+int f32_launch_contig_dit(const f32::Fast32Params &p, int bits, int mode, int kind, int grid, void *stream);
+int f32_launch_strided(const f32::Fast32Params &p, int g, bool dit, int mode, int kind, int grid, void *stream);
+
+}  // namespace intfft

@@ -1,0 +1,8 @@
+// 32-bit-lane kernels, contiguous pass, DIF instantiations (see intfft_fast32.cuh)
+#include "intfft_fast32.cuh"
+namespace intfft {
+int f32_launch_contig_dif(const f32::Fast32Params &p, int bits, int mode, int kind, int grid, void *stream)
+{
+    return (int)f32::launch_contig_n<false>(p, bits, mode, kind, grid, reinterpret_cast<cudaStream_t>(stream));
+}
+}  // namespace intfft

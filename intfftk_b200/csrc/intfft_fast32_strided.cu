@@ -1,0 +1,74 @@
+// 32-bit-lane kernels: strided-pass instantiations and the host-side dispatcher (see intfft_fast32.cuh)
+#include "intfft_fast32.cuh"
+
+namespace intfft {
+
+int f32_launch_strided(const f32::Fast32Params &p, int g, bool dit, int mode, int kind, int grid, void *stream)
+{
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (g == 4) return (int)(dit ? f32::launch_strided<4, true>(p, mode, kind, grid, st) : f32::launch_strided<4, false>(p, mode, kind, grid, st));
+    if (g == 8) return (int)(dit ? f32::launch_strided<8, true>(p, mode, kind, grid, st) : f32::launch_strided<8, false>(p, mode, kind, grid, st));
+    return (int)cudaErrorInvalidValue;
+}
+
+// plans whose every intermediate fits 32-bit lanes (ROUNDING needs one carry bit) and NFFT >= 8
+bool fast32_supported(const intfft_generics &g)
+{
+    if (!g.use_fly || g.nfft_log2 < 8) return false;
+    const int worst = g.data_width + g.format * g.nfft_log2 + ((!g.format && g.rndmode) ? 1 : 0);
+    return worst <= 32;
+}
+
+int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
+                  int num_sms, void *stream)
+{
+    f32::Fast32Params p{};
+    p.in = pd.kp.in;
+    p.out = pd.kp.out;
+    p.tw = tw;
+    p.total = pd.kp.total;
+    p.n = pd.kp.n;
+    p.batch = pd.kp.total >> pd.kp.n;
+    p.n_tiles = (pd.kp.total + 4095) >> 12;
+    p.dw = pd.kp.dw;
+    p.format = pd.kp.format;
+    p.in_sb = pd.kp.in_sb;
+    p.out_sb = pd.kp.out_sb;
+    p.in_wrap = pd.kp.in_wrap;
+    p.cm = pd.kp.cm;
+    for (int i = 0; i < 16; ++i) { p.lw_r[i] = lw_r[i]; p.lw_i[i] = lw_i[i]; }
+    // multiplier arrangement policy: all stages of this pass single-DSP, or decided per stage
+    int kind = f32::KIND_SINGLE;
+    {
+        const int n = pd.kp.n, fmt = pd.kp.format;
+        for (int b = pd.kp.pb; b < pd.kp.pb + pd.kp.g; ++b) {
+            const int ii = dit ? b : n - 1 - b;
+            const int dtw = pd.kp.dw + ii * fmt;
+            const int dtwc = dit ? dtw : dtw + fmt;
+            if (b >= 2 && dtwc >= pd.kp.cm.lim_single) kind = f32::KIND_MIXED;
+        }
+    }
+    long long grid = 2ll * num_sms;
+    int e = (int)cudaErrorInvalidValue;
+    if (pd.kp.c == 0) {
+        if (grid > p.n_tiles) grid = p.n_tiles;
+        if (grid < 1) grid = 1;
+        e = dit ? f32_launch_contig_dit(p, pd.kp.g, mode, kind, (int)grid, stream)
+                : f32_launch_contig_dif(p, pd.kp.g, mode, kind, (int)grid, stream);
+    } else {
+        const int G = pd.kp.g, C = 12 - G, mid_bits = p.n - G - C;
+        const long long mids = 1ll << mid_bits;
+        long long chunks = (8 * grid + mids - 1) / mids;
+        if (chunks < 1) chunks = 1;
+        if (chunks > p.batch) chunks = p.batch;
+        p.frames_per_unit = (int)((p.batch + chunks - 1) / chunks);
+        chunks = (p.batch + p.frames_per_unit - 1) / p.frames_per_unit;
+        p.n_units = mids * chunks;
+        if (grid > p.n_units) grid = p.n_units;
+        e = f32_launch_strided(p, G, dit, mode, kind, (int)grid, stream);
+    }
+    count_launch();
+    return (int)e;
+}
+
+}  // namespace intfft

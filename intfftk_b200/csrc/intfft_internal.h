@@ -56,7 +56,7 @@ struct PassDesc {
     int threads;
     size_t smem_bytes;
     int scratch_in, scratch_out;  // -1 = user buffer, else index of plan scratch buffer
-    bool fast16;           // handled by the specialised packed-16 kernel
+    int path;              // 0 generic tile kernel, 1 packed-16 kernels, 2 32-bit-lane kernels
 };
 
 struct Plan {
@@ -69,6 +69,7 @@ struct Plan {
     int2 *d_tw = nullptr;        // device twiddle table (int32 pairs)
     int2 *d_twp = nullptr;       // twiddles pre-shifted for the 32-bit-product kernel (fast16 plans only)
     int lw_r[16] = {0}, lw_i[16] = {0};  // its lowest-round twiddles (stages 2, 3)
+    int lw32_r[16] = {0}, lw32_i[16] = {0};  // same, not pre-shifted (32-bit-lane kernels)
     void *scratch[2] = {nullptr, nullptr};
     size_t scratch_bytes[2] = {0, 0};
     void *h2d = nullptr, *d2h = nullptr;  // device staging for intfft_exec_host
@@ -83,6 +84,9 @@ int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const
                   int num_sms, void *stream);
 bool fast16_supported(const intfft_generics &g);
 int launch_fast16_strided(const PassDesc &pd, bool dit, const int2 *twp, int num_sms, void *stream);
+bool fast32_supported(const intfft_generics &g);
+int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
+                  int num_sms, void *stream);
 int launch_bypass(const void *in, void *out, long long n_scalars, int in_sb, int out_sb, int dw,
                   int zero_extend, void *stream);
 int launch_bitrev(int nfft_log2, int scalar_bytes, long long batch, const void *in, void *out, void *stream);

