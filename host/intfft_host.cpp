@@ -6,8 +6,14 @@
 // tb/fft_signle_test.vhd:158-165: one "re im" pair of decimal integers per line, frames back to back.
 // Output: same format, flat stream order (FFT: bit-reversed, IFFT: natural), one frame after another.
 //
-// usage: intfft_host [--ifft] [--nfft N] [--dw W] [--tw W] [--mode UNSCALED|ROUNDING|TRUNCATE]
-//                    [--xser OLD|NEW] [--no-fly] <in.dat> <out.dat>
+// --lanes switches both files to the two-lane testbench format of tb/fft_double_test.vhd:154-161,207-214
+// (math/di_double.dat / dout_pair.dat): one beat per line, "lane0_re lane1_re lane0_im lane1_im"; the
+// lanes are the core's own (FFT: halves in, even/odd out; IFFT: even/odd in, halves out; pair: halves
+// both ways).  --top17 dumps only the 17 most significant bits of every output, as that testbench does.
+// --pair runs int_fft_ifft_pair (FFT then IFFT on DATA_WIDTH + FORMAT*NFFT bits) instead of one core.
+//
+// usage: intfft_host [--ifft | --pair] [--nfft N] [--dw W] [--tw W] [--mode UNSCALED|ROUNDING|TRUNCATE]
+//                    [--xser OLD|NEW] [--no-fly] [--lanes] [--top17] <in.dat> <out.dat>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,16 +22,45 @@
 
 #include "intfft.h"
 
+// int_fft_ifft_pair through host buffers, using only the C-ABI: device staging comes from two throw-away
+// one-core plans' exec_host (FFT to host, IFFT from host) when no CUDA runtime is linked into this tool.
+static int run_pair_host(intfft_pair *, const intfft_layout &lay, const void *h_in, void *h_out);
+
 static int fail(const char *what, int st)
 {
     std::fprintf(stderr, "intfft_host: %s: %s\n", what, intfft_strerror(st));
     return 1;
 }
 
+static intfft_generics g_for_pair;
+static long long frames_for_pair;
+static int run_pair_host(intfft_pair *, const intfft_layout &lay, const void *h_in, void *h_out)
+{
+    intfft_generics gf = g_for_pair, gi = g_for_pair;
+    gf.direction = 0;
+    gi.direction = 1;
+    gi.data_width = gf.data_width + gf.format * gf.nfft_log2;        // int_fft_ifft_pair.vhd:261
+    intfft_plan *pf = nullptr, *pi = nullptr;
+    int st = intfft_plan_create(&pf, &gf, frames_for_pair, 0);
+    if (!st) st = intfft_plan_create(&pi, &gi, frames_for_pair, 0);
+    if (!st) {
+        intfft_layout lf;
+        intfft_query(pf, &lf);
+        std::vector<unsigned char> mid((size_t)lf.out_bytes);
+        st = intfft_exec_host(pf, h_in, mid.data());
+        if (!st) st = intfft_exec_host(pi, mid.data(), h_out);
+    }
+    if (pf) intfft_plan_destroy(pf);
+    if (pi) intfft_plan_destroy(pi);
+    (void)lay;
+    return st;
+}
+
 int main(int argc, char **argv)
 {
     intfft_generics g{7, 16, 16, 1, 0, 1, 1, 0};   // the testbench defaults: NFFT=7, 16/16, XSERIES="NEW"
     std::string in_path, out_path;
+    bool lanes = false, top17 = false, pair = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&](const char *name) -> const char * {
@@ -33,6 +68,9 @@ int main(int argc, char **argv)
             return argv[++i];
         };
         if (a == "--ifft") g.direction = 1;
+        else if (a == "--pair") pair = true;
+        else if (a == "--lanes") lanes = true;
+        else if (a == "--top17") top17 = true;
         else if (a == "--nfft") g.nfft_log2 = std::atoi(next("--nfft"));
         else if (a == "--dw") g.data_width = std::atoi(next("--dw"));
         else if (a == "--tw") g.twdl_width = std::atoi(next("--tw"));
@@ -54,40 +92,78 @@ int main(int argc, char **argv)
     int st = intfft_validate(&g);
     if (st) return fail("generics", st);
 
+    const long long n = 1ll << g.nfft_log2;
+    // lane <-> flat index maps of the cores (int_fftNk.vhd:15-21, int_ifftNk.vhd:15-21)
+    auto flat_of = [&](bool halves, int lane, long long beat) { return halves ? lane * (n / 2) + beat : 2 * beat + lane; };
+    const bool in_halves = pair || g.direction == 0, out_halves = pair || g.direction == 1;
+
     std::vector<long long> vals;
     if (FILE *f = std::fopen(in_path.c_str(), "r")) {
-        long long re, im;
-        while (std::fscanf(f, "%lld %lld", &re, &im) == 2) { vals.push_back(re); vals.push_back(im); }
+        long long a, b, c, d;
+        if (!lanes) {
+            while (std::fscanf(f, "%lld %lld", &a, &b) == 2) { vals.push_back(a); vals.push_back(b); }
+        } else {
+            std::vector<long long> beats;
+            while (std::fscanf(f, "%lld %lld %lld %lld", &a, &b, &c, &d) == 4) { beats.insert(beats.end(), {a, b, c, d}); }
+            const long long nb = (long long)beats.size() / 4, fr = nb / (n / 2);
+            vals.assign((size_t)fr * n * 2, 0);
+            for (long long fi = 0; fi < fr; ++fi)
+                for (long long p = 0; p < n / 2; ++p) {
+                    const long long *q = &beats[(size_t)(fi * (n / 2) + p) * 4];
+                    const long long i0 = fi * n + flat_of(in_halves, 0, p), i1 = fi * n + flat_of(in_halves, 1, p);
+                    vals[2 * i0] = q[0]; vals[2 * i1] = q[1]; vals[2 * i0 + 1] = q[2]; vals[2 * i1 + 1] = q[3];
+                }
+        }
         std::fclose(f);
     } else { std::perror(in_path.c_str()); return 1; }
-    const long long n = 1ll << g.nfft_log2;
     const long long frames = (long long)vals.size() / (2 * n);
     if (frames < 1) { std::fprintf(stderr, "need at least one frame of %lld samples\n", n); return 1; }
 
+    g_for_pair = g;
+    frames_for_pair = frames;
     intfft_plan *plan = nullptr;
-    st = intfft_plan_create(&plan, &g, frames, 0);
-    if (st) return fail("plan_create", st);
+    intfft_pair *pr = nullptr;
     intfft_layout lay;
-    intfft_query(plan, &lay);
+    if (pair) {
+        st = intfft_pair_create(&pr, &g, 1, frames, 0);
+        if (st) return fail("pair_create", st);
+        intfft_pair_query(pr, &lay);
+    } else {
+        st = intfft_plan_create(&plan, &g, frames, 0);
+        if (st) return fail("plan_create", st);
+        intfft_query(plan, &lay);
+    }
     std::vector<unsigned char> hin((size_t)lay.in_bytes), hout((size_t)lay.out_bytes);
     for (long long i = 0; i < frames * n * 2; ++i) {
         if (lay.in_scalar_bytes == 2) reinterpret_cast<int16_t *>(hin.data())[i] = (int16_t)vals[i];
         else if (lay.in_scalar_bytes == 4) reinterpret_cast<int32_t *>(hin.data())[i] = (int32_t)vals[i];
         else reinterpret_cast<int64_t *>(hin.data())[i] = vals[i];
     }
-    st = intfft_exec_host(plan, hin.data(), hout.data());
-    if (st) return fail("exec_host", st);
+    if (pair) st = run_pair_host(pr, lay, hin.data(), hout.data());
+    else st = intfft_exec_host(plan, hin.data(), hout.data());
+    if (st) return fail("exec", st);
+    auto out_scalar = [&](long long i) -> long long {
+        long long v;
+        if (lay.out_scalar_bytes == 2) v = reinterpret_cast<int16_t *>(hout.data())[i];
+        else if (lay.out_scalar_bytes == 4) v = reinterpret_cast<int32_t *>(hout.data())[i];
+        else v = reinterpret_cast<int64_t *>(hout.data())[i];
+        return top17 && lay.out_width > 17 ? v >> (lay.out_width - 17) : v;   // slice (W-1 downto W-17)
+    };
     FILE *o = std::fopen(out_path.c_str(), "w");
     if (!o) { std::perror(out_path.c_str()); return 1; }
-    for (long long i = 0; i < frames * n; ++i) {
-        long long re, im;
-        if (lay.out_scalar_bytes == 2) { re = reinterpret_cast<int16_t *>(hout.data())[2 * i]; im = reinterpret_cast<int16_t *>(hout.data())[2 * i + 1]; }
-        else if (lay.out_scalar_bytes == 4) { re = reinterpret_cast<int32_t *>(hout.data())[2 * i]; im = reinterpret_cast<int32_t *>(hout.data())[2 * i + 1]; }
-        else { re = reinterpret_cast<int64_t *>(hout.data())[2 * i]; im = reinterpret_cast<int64_t *>(hout.data())[2 * i + 1]; }
-        std::fprintf(o, "%lld %lld\n", re, im);
+    if (!lanes) {
+        for (long long i = 0; i < frames * n; ++i) std::fprintf(o, "%lld %lld\n", out_scalar(2 * i), out_scalar(2 * i + 1));
+    } else {
+        for (long long fi = 0; fi < frames; ++fi)
+            for (long long p = 0; p < n / 2; ++p) {
+                const long long i0 = fi * n + flat_of(out_halves, 0, p), i1 = fi * n + flat_of(out_halves, 1, p);
+                std::fprintf(o, "%lld    %lld    %lld    %lld\n", out_scalar(2 * i0), out_scalar(2 * i1),
+                             out_scalar(2 * i0 + 1), out_scalar(2 * i1 + 1));
+            }
     }
     std::fclose(o);
-    intfft_plan_destroy(plan);
+    if (plan) intfft_plan_destroy(plan);
+    if (pr) intfft_pair_destroy(pr);
     std::fprintf(stderr, "intfft_host: %lld frame(s) of %lld points, %d-bit in, %d-bit out\n", frames, n,
                  lay.in_width, lay.out_width);
     return 0;

@@ -98,6 +98,17 @@ int intfft_exec_host(intfft_plan *p, const void *h_in, void *h_out);
  * (rom_twiddle_int.vhd:98-248); stage >= 2.  Host-only, needs no device. */
 int intfft_twiddles(const intfft_generics *g, int stage, int32_t *h_re, int32_t *h_im);
 
+/* f2: the FFT -> IFFT loop-back of int_fft_ifft_pair (main/int_fft_ifft_pair.vhd:209-283):
+ * int_fftNk(generics) feeding int_ifftNk with DATA_WIDTH + FORMAT*NFFT input bits (:261), natural order in,
+ * natural order out, output width DATA_WIDTH + 2*FORMAT*NFFT (:98-101).  g->use_fly is FLY_FWD, fly_inv is
+ * FLY_INV (:91-92); g->direction is ignored.  Specified on the core lanes (flat in-place order), not on the
+ * wrapper's interleave-2 I/O buffers.  The spectrum stays on the device between the two cores. */
+typedef struct intfft_pair intfft_pair;
+int intfft_pair_create(intfft_pair **out, const intfft_generics *g, int fly_inv, int64_t batch, int device);
+int intfft_pair_destroy(intfft_pair *p);
+int intfft_pair_query(const intfft_pair *p, intfft_layout *l);
+int intfft_pair_exec(intfft_pair *p, const void *d_in, void *d_out, void *cuda_stream);
+
 /* f1: bit-reversal reorder of a batch of frames, the job int_bitrev_order does in
  * int_fft_single_path (buffers/int_bitrev_order.vhd:82-104): out[bitrev(q)] = in[q].
  * scalar_bytes in {2,4,8}; d_in != d_out. */

@@ -56,6 +56,10 @@ def lib() -> ctypes.CDLL:
         L.intfft_exec.argtypes = [vp, vp, vp, vp]
         L.intfft_exec_host.argtypes = [vp, vp, vp]
         L.intfft_twiddles.argtypes = [P(_CGenerics), ctypes.c_int, vp, vp]
+        L.intfft_pair_create.argtypes = [P(vp), P(_CGenerics), ctypes.c_int, ctypes.c_int64, ctypes.c_int]
+        L.intfft_pair_destroy.argtypes = [vp]
+        L.intfft_pair_query.argtypes = [vp, P(_CLayout)]
+        L.intfft_pair_exec.argtypes = [vp, vp, vp, vp]
         L.intfft_bitrev.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, vp, vp, ctypes.c_int, vp]
         L.intfft_fill_random.argtypes = [vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
                                          ctypes.c_int, vp]
@@ -200,6 +204,43 @@ class Core:
         st = lib().intfft_exec_host(self._h, h_in_ptr, h_out_ptr)
         if st:
             raise IntfftError(st, "intfft_exec_host")
+
+
+class Pair:
+    """int_fft_ifft_pair on the core lanes: int_fftNk -> int_ifftNk(DATA_WIDTH + FORMAT*NFFT), natural order in
+    and out (main/int_fft_ifft_pair.vhd:209-283).  FLY_FWD = generics.USE_FLY, FLY_INV = fly_inv."""
+
+    def __init__(self, generics: Generics, batch: int, fly_inv: int = 1, device: int = 0):
+        self.generics, self.device = generics, device
+        self._h = ctypes.c_void_p()
+        c = generics.c_struct(0)
+        st = lib().intfft_pair_create(ctypes.byref(self._h), ctypes.byref(c), fly_inv, batch, device)
+        if st:
+            self._h = ctypes.c_void_p()
+            raise IntfftError(st, "intfft_pair_create")
+        lay = _CLayout()
+        lib().intfft_pair_query(self._h, ctypes.byref(lay))
+        self.layout, self.n, self.batch = lay, int(lay.n), int(lay.batch)
+        self.in_dtype, self.out_dtype = scalar_dtype(lay.in_width), scalar_dtype(lay.out_width)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().intfft_pair_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def exec(self, d_in, d_out=None, stream=None):
+        import torch
+        if d_out is None:
+            d_out = torch.empty((self.batch, self.n, 2), dtype=_torch_dtype(self.out_dtype), device=d_in.device)
+        assert d_in.is_cuda and d_in.is_contiguous() and d_in.element_size() == self.layout.in_scalar_bytes
+        assert d_out.element_size() == self.layout.out_scalar_bytes and d_out.numel() == self.batch * self.n * 2
+        s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        st = lib().intfft_pair_exec(self._h, d_in.data_ptr(), d_out.data_ptr(), s)
+        if st:
+            raise IntfftError(st, "intfft_pair_exec")
+        return d_out
 
 
 def _torch_dtype(np_dtype):

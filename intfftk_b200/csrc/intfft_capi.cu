@@ -347,6 +347,71 @@ int intfft_exec_host(intfft_plan *p, const void *h_in, void *h_out)
     return cudaGetLastError() == cudaSuccess ? INTFFT_OK : INTFFT_ECUDA;
 }
 
+// ---- f2: int_fft_ifft_pair ----------------------------------------------------------------------
+struct intfft_pair {
+    intfft_plan *fwd = nullptr, *inv = nullptr;
+    void *mid = nullptr;           // spectrum between the two cores (bit-reversed order), device
+};
+
+int intfft_pair_create(intfft_pair **out, const intfft_generics *g, int fly_inv, int64_t batch, int device)
+{
+    if (!out || !g || (fly_inv | 1) != 1) return INTFFT_EINVAL;
+    *out = nullptr;
+    intfft_generics gf = *g, gi = *g;
+    gf.direction = 0;
+    gi.direction = 1;
+    gi.use_fly = fly_inv;
+    gi.data_width = g->data_width + g->format * g->nfft_log2;      // int_fft_ifft_pair.vhd:261
+    int st = validate(&gf);
+    if (!st) st = validate(&gi);
+    if (st) return st;
+    intfft_pair *p = new (std::nothrow) intfft_pair();
+    if (!p) return INTFFT_ENOMEM;
+    st = intfft_plan_create(&p->fwd, &gf, batch, device);
+    if (!st) st = intfft_plan_create(&p->inv, &gi, batch, device);
+    if (!st) {
+        DeviceGuard guard(device);
+        intfft_layout l;
+        intfft_query(p->fwd, &l);
+        if (cudaMalloc(&p->mid, (size_t)l.out_bytes) != cudaSuccess) st = INTFFT_ENOMEM;
+    }
+    if (st) { intfft_pair_destroy(p); return st; }
+    *out = p;
+    return INTFFT_OK;
+}
+
+int intfft_pair_destroy(intfft_pair *p)
+{
+    if (!p) return INTFFT_EINVAL;
+    if (p->mid && p->fwd) { DeviceGuard guard(p->fwd->device); cudaFree(p->mid); }
+    if (p->fwd) intfft_plan_destroy(p->fwd);
+    if (p->inv) intfft_plan_destroy(p->inv);
+    delete p;
+    return INTFFT_OK;
+}
+
+int intfft_pair_query(const intfft_pair *p, intfft_layout *l)
+{
+    if (!p || !l) return INTFFT_EINVAL;
+    intfft_layout a, b;
+    intfft_query(p->fwd, &a);
+    intfft_query(p->inv, &b);
+    *l = a;
+    l->out_width = b.out_width;
+    l->out_scalar_bytes = b.out_scalar_bytes;
+    l->out_bytes = b.out_bytes;
+    l->n_passes = a.n_passes + b.n_passes;
+    l->lane_bits = a.lane_bits > b.lane_bits ? a.lane_bits : b.lane_bits;
+    return INTFFT_OK;
+}
+
+int intfft_pair_exec(intfft_pair *p, const void *d_in, void *d_out, void *cuda_stream)
+{
+    if (!p || !d_in || !d_out) return INTFFT_EINVAL;
+    const int st = intfft_exec(p->fwd, d_in, p->mid, cuda_stream);
+    return st ? st : intfft_exec(p->inv, p->mid, d_out, cuda_stream);
+}
+
 int intfft_twiddles(const intfft_generics *g, int stage, int32_t *h_re, int32_t *h_im)
 {
     if (!g || !h_re || !h_im || stage < 2 || stage > 19) return INTFFT_EINVAL;

@@ -202,6 +202,58 @@ def test_rounding_difference_wrap_edge(ib, oracle):
             assert np.array_equal(got, want), (nfft, dw, direction)
 
 
+@pytest.mark.parametrize("kw", [dict(NFFT=7, DATA_WIDTH=16, FORMAT=1), dict(NFFT=12, DATA_WIDTH=16, FORMAT=0),
+                                dict(NFFT=10, DATA_WIDTH=12, FORMAT=1, XSER="OLD"), dict(NFFT=9, DATA_WIDTH=18, FORMAT=0, RNDMODE=1),
+                                dict(NFFT=14, DATA_WIDTH=16, FORMAT=0)])
+def test_fft_ifft_pair(ib, oracle, kw):
+    """f2: int_fft_ifft_pair = int_fftNk -> int_ifftNk(DATA_WIDTH + FORMAT*NFFT), spectrum kept on the device."""
+    g = ib.Generics(**kw)
+    n, batch = 1 << g.NFFT, 5
+    xs = 1 if g.XSER == "NEW" else 0
+    x = oracle.fill_random(batch * n * 2, g.DATA_WIDTH - 1, 11).reshape(batch, n, 2)     # one bit of headroom
+    x = x.astype(oracle.scalar_dtype(g.DATA_WIDTH))
+    mid = oracle.batch(oracle.generics(g.NFFT, g.DATA_WIDTH, g.TWDL_WIDTH, g.FORMAT, g.RNDMODE, xs, 1, 0), x)
+    want = oracle.batch(oracle.generics(g.NFFT, g.out_width, g.TWDL_WIDTH, g.FORMAT, g.RNDMODE, xs, 1, 1), mid)
+    pair = ib.Pair(g, batch)
+    got = pair.exec(torch.from_numpy(x).cuda()).cpu().numpy()
+    pair.close()
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+
+
+def test_cpp_host_replays_testbench_files(ib, oracle, tmp_path):
+    """f3: host/intfft_host.cpp (stand-in for src/vhdl/tb/*.vhd) with the reference's file formats:
+    di_single.dat ("re im" per line, math/fft_single.m:94-98) and the two-lane four-column format of
+    di_double.dat / dout_pair.dat (tb/fft_double_test.vhd:154-161, 207-214)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "intfftk_b200", "intfft_host")
+    assert os.path.exists(exe), "intfft_host not built"
+    nfft, n, frames = 7, 128, 3
+    x = oracle.fill_random(frames * n * 2, 15, 42).reshape(frames, n, 2).astype(np.int16)
+    # --- single-lane format, three testbench modes
+    np.savetxt(tmp_path / "di_single.dat", x.reshape(-1, 2), fmt="%d")
+    for mode, (fmt, rnd) in (("UNSCALED", (1, 0)), ("ROUNDING", (0, 1)), ("TRUNCATE", (0, 0))):
+        subprocess.check_call([exe, "--nfft", str(nfft), "--mode", mode, str(tmp_path / "di_single.dat"), str(tmp_path / "do.dat")])
+        got = np.loadtxt(tmp_path / "do.dat", dtype=np.int64).reshape(frames, n, 2)
+        want = oracle.batch(oracle.generics(nfft, 16, 16, fmt, rnd, 1, 1, 0), x)
+        assert np.array_equal(got, want.astype(np.int64)), mode
+    # --- two-lane format: FFT (halves in, even/odd out)
+    beats = np.stack([x[:, : n // 2, 0], x[:, n // 2:, 0], x[:, : n // 2, 1], x[:, n // 2:, 1]], -1).reshape(-1, 4)
+    np.savetxt(tmp_path / "di_double.dat", beats, fmt="%d")
+    subprocess.check_call([exe, "--nfft", str(nfft), "--mode", "UNSCALED", "--lanes", str(tmp_path / "di_double.dat"), str(tmp_path / "do2.dat")])
+    got = np.loadtxt(tmp_path / "do2.dat", dtype=np.int64).reshape(frames, n // 2, 4)
+    want = oracle.batch(oracle.generics(nfft, 16, 16, 1, 0, 1, 1, 0), x).astype(np.int64)
+    assert np.array_equal(got[..., 0], want[:, 0::2, 0]) and np.array_equal(got[..., 1], want[:, 1::2, 0])
+    assert np.array_equal(got[..., 2], want[:, 0::2, 1]) and np.array_equal(got[..., 3], want[:, 1::2, 1])
+    # --- int_fft_ifft_pair with the top-17-bit dump of fft_double_test
+    subprocess.check_call([exe, "--nfft", str(nfft), "--mode", "UNSCALED", "--pair", "--lanes", "--top17",
+                           str(tmp_path / "di_double.dat"), str(tmp_path / "dout_pair.dat")])
+    got = np.loadtxt(tmp_path / "dout_pair.dat", dtype=np.int64).reshape(frames, n // 2, 4)
+    mid = oracle.batch(oracle.generics(nfft, 16, 16, 1, 0, 1, 1, 0), x)
+    fin = oracle.batch(oracle.generics(nfft, 16 + nfft, 16, 1, 0, 1, 1, 1), mid).astype(np.int64) >> (16 + 2 * nfft - 17)
+    assert np.array_equal(got[..., 0], fin[:, : n // 2, 0]) and np.array_equal(got[..., 1], fin[:, n // 2:, 0])
+    assert np.array_equal(got[..., 2], fin[:, : n // 2, 1]) and np.array_equal(got[..., 3], fin[:, n // 2:, 1])
+
+
 def test_use_fly_bypass(ib, oracle):
     for fmt in (0, 1):
         got, want = _run_both(ib, oracle, 5, seed=3, NFFT=9, DATA_WIDTH=12, FORMAT=fmt, USE_FLY=0)
