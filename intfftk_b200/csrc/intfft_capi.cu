@@ -277,7 +277,7 @@ static int exec_frames(intfft_plan *p, const void *d_in, void *d_out, long long 
         pd.kp.n_tiles = pd.kp.c > 0 ? (frames << (n - pd.kp.L)) : ((total + (1ll << pd.kp.L) - 1) >> pd.kp.L);
         int e;
         if (pd.path == 1)
-            e = pd.kp.c > 0 ? launch_fast16_strided(pd, dit, p->d_twp, p->num_sms, cuda_stream)
+            e = pd.kp.c > 0 ? launch_fast16_strided(pd, p->mode, dit, p->d_twp, p->num_sms, cuda_stream)
                             : launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream);
         else if (pd.path == 2)
             e = launch_fast32(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);

@@ -91,14 +91,33 @@ __device__ __forceinline__ int negq(int v) { return (v >> 31) - v; }
 
 // RAWY (DIF, DW16 only): leave Y as the raw 32-bit sum of products; its value is raw >> 16, which the
 // packer takes straight from the upper half-words (PRMT 0x7632) instead of two shifts + PRMT.
-template <bool DIT, bool DW16, bool RAWY = false>
+// ROUNDING helpers: (v + 1) >> 1 == (v >> 1) + v(0); the rounded DIFFERENCE can reach 2^(DW-1) and is kept
+// in DW bits by the reference (int_dif2_fly.vhd:201-216), hence the sign-extension from bit DW-1
+template <bool DW16> __device__ __forceinline__ int rnd_sum(int a, int b) { return sra<1>(a + b + 1); }
+template <bool DW16> __device__ __forceinline__ int rnd_dif(int a, int b, int sh_full)
+{
+    const int d = sra<1>(a - b + 1);
+    return DW16 ? sext_lo16((uint32_t)d) : ((int)((unsigned)d << sh_full) >> sh_full);
+}
+
+template <bool DIT, bool DW16, int MODE, bool RAWY = false>
 __device__ __forceinline__ void fly(int s, bool odd, int &ar, int &ai, int &br, int &bi, int wr, int wi,
                                     int sh_full, int sh_half)
 {
     if (!DIT) {
-        const int tr = sra<1>(br), ti = sra<1>(bi);
-        const int xr = sra<1>(ar) + tr, xi = sra<1>(ai) + ti;
-        const int sr = msub2(tr, xr), si = msub2(ti, xi);       // (A>>1) - (B>>1)
+        int xr, xi, sr, si;
+        if (MODE == MODE_TRUNC) {
+            const int tr = sra<1>(br), ti = sra<1>(bi);
+            xr = sra<1>(ar) + tr;
+            xi = sra<1>(ai) + ti;
+            sr = msub2(tr, xr);                                  // (A>>1) - (B>>1)
+            si = msub2(ti, xi);
+        } else {
+            xr = rnd_sum<DW16>(ar, br);
+            xi = rnd_sum<DW16>(ai, bi);
+            sr = rnd_dif<DW16>(ar, br, sh_full);
+            si = rnd_dif<DW16>(ai, bi, sh_full);
+        }
         ar = xr;
         ai = xi;
         if (s == 0) {
@@ -113,7 +132,7 @@ __device__ __forceinline__ void fly(int s, bool odd, int &ar, int &ai, int &br, 
             br = RAWY ? pr : (DW16 ? sra<16>(pr) : (pr >> sh_full));
             bi = RAWY ? pi : (DW16 ? sra<16>(pi) : (pi >> sh_full));
         }
-    } else {
+    } else if (MODE == MODE_TRUNC) {
         int hr, hi;                                             // BW >> 1
         if (s == 0) {
             hr = sra<1>(br);
@@ -132,11 +151,30 @@ __device__ __forceinline__ void fly(int s, bool odd, int &ar, int &ai, int &br, 
         bi = msub2(hi, xi);
         ar = xr;
         ai = xi;
+    } else {                                                    // ROUNDING, DIT
+        int wr_, wi_;                                           // BW
+        if (s == 0) {
+            wr_ = br;
+            wi_ = bi;
+        } else if (s == 1) {
+            wr_ = odd ? negq(bi) : br;
+            wi_ = odd ? br : bi;
+        } else {
+            const int o_re = (int)((unsigned)bi * (unsigned)wr - (unsigned)br * (unsigned)wi);
+            const int o_im = (int)((unsigned)bi * (unsigned)wi + (unsigned)br * (unsigned)wr);
+            wi_ = DW16 ? sra<16>(o_re) : (o_re >> sh_full);
+            wr_ = DW16 ? sra<16>(o_im) : (o_im >> sh_full);
+        }
+        const int xr = rnd_sum<DW16>(ar, wr_), xi = rnd_sum<DW16>(ai, wi_);
+        br = rnd_dif<DW16>(ar, wr_, sh_full);
+        bi = rnd_dif<DW16>(ai, wi_, sh_full);
+        ar = xr;
+        ai = xi;
     }
 }
 
 // R stages (global bits LO .. LO+R-1) on the 16 register-resident samples
-template <int LO, int R, bool DIT, bool DW16, bool RAWLAST, typename TW>
+template <int LO, int R, bool DIT, bool DW16, int MODE, bool RAWLAST, typename TW>
 __device__ __forceinline__ void round_regs(int (&re)[16], int (&im)[16], const TW &tw, bool tid_odd, int sh_full,
                                            int sh_half)
 {
@@ -152,9 +190,9 @@ __device__ __forceinline__ void round_regs(int (&re)[16], int (&im)[16], const T
             int wr = 0, wi = 0;
             if (LO + q >= 2) tw(w, wr, wi);
             if (RAWLAST && step == R - 1)
-                fly<DIT, DW16, true>(LO + q, odd, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi, sh_full, sh_half);
+                fly<DIT, DW16, MODE, true>(LO + q, odd, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi, sh_full, sh_half);
             else
-                fly<DIT, DW16>(LO + q, odd, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi, sh_full, sh_half);
+                fly<DIT, DW16, MODE>(LO + q, odd, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi, sh_full, sh_half);
         }
     }
 }
@@ -177,7 +215,7 @@ struct TwSmem {          // table[w][tid & 15] of pre-shifted (re, im); one LDS.
 
 // MIDSM: keep the middle round's 15 twiddles in a 1920-byte shared table instead of 30 registers, which
 // brings the kernel under 85 registers so that three CTAs (24 warps) fit on one SM.
-template <int NLOG2, bool DIT, bool DW16, bool MIDSM>
+template <int NLOG2, bool DIT, bool DW16, bool MIDSM, int MODE>
 __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid_constant__ Fast16Params p)
 {
     constexpr int R0 = ((NLOG2 - 1) % 4) + 1;      // stages in the lowest round
@@ -302,10 +340,10 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
             // DIF upper rounds end with a multiply stage on register bit 0 (global bit >= 2): odd registers
             // then hold raw products and are packed from their upper half-words
             constexpr bool RAW = !DIT && DW16 && R0 >= 2;
-            if (r == 0) round_regs<0, R0, DIT, DW16, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
-            else if (r == 1 && MIDSM) round_regs<R0, 4, DIT, DW16, RAW>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
-            else if (r == 1) round_regs<R0, 4, DIT, DW16, RAW>(re, im, TwRegs{uwr[0], uwi[0]}, tid_odd, sh_full, sh_half);
-            else round_regs<R0 + 4, 4, DIT, DW16, RAW>(re, im, TwRegs{uwr[NR - 2], uwi[NR - 2]}, tid_odd, sh_full, sh_half);
+            if (r == 0) round_regs<0, R0, DIT, DW16, MODE, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
+            else if (r == 1 && MIDSM) round_regs<R0, 4, DIT, DW16, MODE, RAW>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
+            else if (r == 1) round_regs<R0, 4, DIT, DW16, MODE, RAW>(re, im, TwRegs{uwr[0], uwi[0]}, tid_odd, sh_full, sh_half);
+            else round_regs<R0 + 4, 4, DIT, DW16, MODE, RAW>(re, im, TwRegs{uwr[NR - 2], uwi[NR - 2]}, tid_odd, sh_full, sh_half);
 
             // ---- hand the samples on: to the exchange tile, or to HBM after the last round ----
             if (r == 0 && R0 == 4) {
@@ -360,7 +398,7 @@ struct Strided16Params {
     int dw, sh_full, sh_half;
 };
 
-template <int G, bool DIT, bool DW16>
+template <int G, bool DIT, bool DW16, int MODE>
 __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_constant__ Strided16Params p)
 {
     constexpr int C = 12 - G;                       // log2 contiguous columns per tile
@@ -427,8 +465,8 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
                     unpack<DW16>(x, p.dw, re[m], im[m]);
                 }
                 constexpr bool RAW = !DIT && DW16;
-                if (lo == 8) round_regs<8, 4, DIT, DW16, RAW && (NR == 2)>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
-                else round_regs<4, 4, DIT, DW16, false>(re, im, TwSmem{midtw + (tid & 15u)}, false, sh_full, sh_half);
+                if (lo == 8) round_regs<8, 4, DIT, DW16, MODE, RAW && (NR == 2)>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
+                else round_regs<4, 4, DIT, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, false, sh_full, sh_half);
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
                     const unsigned l = base | ((unsigned)m << lo);
@@ -447,10 +485,10 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
 }
 
 template <int G, bool DIT, bool DW16>
-cudaError_t launch_strided_k(const Strided16Params &p, int grid, cudaStream_t st)
+cudaError_t launch_strided_k(const Strided16Params &p, int mode, int grid, cudaStream_t st)
 {
     const int smem = kSmemHead + 2 * kTileWords * 4;
-    auto k = fast16_strided_kernel<G, DIT, DW16>;
+    auto k = mode == MODE_ROUND ? fast16_strided_kernel<G, DIT, DW16, MODE_ROUND> : fast16_strided_kernel<G, DIT, DW16, MODE_TRUNC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, smem, st>>>(p);
@@ -458,11 +496,11 @@ cudaError_t launch_strided_k(const Strided16Params &p, int grid, cudaStream_t st
 }
 
 template <int NLOG2, bool DIT, bool DW16>
-cudaError_t launch_k(const Fast16Params &p, int grid, cudaStream_t st)
+cudaError_t launch_k(const Fast16Params &p, int mode, int grid, cudaStream_t st)
 {
     const int smem = kSmemHead + 2 * kTileWords * 4 + (DIT ? 0 : 2 * 4096 * 4);
     constexpr bool MIDSM = (NLOG2 == 12);
-    auto k = fast16_kernel<NLOG2, DIT, DW16, MIDSM>;
+    auto k = mode == MODE_ROUND ? fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_ROUND> : fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_TRUNC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, smem, st>>>(p);
@@ -470,22 +508,22 @@ cudaError_t launch_k(const Fast16Params &p, int grid, cudaStream_t st)
 }
 
 template <int NLOG2>
-cudaError_t launch_n(const Fast16Params &p, bool dit, bool dw16, int grid, cudaStream_t st)
+cudaError_t launch_n(const Fast16Params &p, int mode, bool dit, bool dw16, int grid, cudaStream_t st)
 {
-    if (!dit) return dw16 ? launch_k<NLOG2, false, true>(p, grid, st) : launch_k<NLOG2, false, false>(p, grid, st);
-    return dw16 ? launch_k<NLOG2, true, true>(p, grid, st) : launch_k<NLOG2, true, false>(p, grid, st);
+    if (!dit) return dw16 ? launch_k<NLOG2, false, true>(p, mode, grid, st) : launch_k<NLOG2, false, false>(p, mode, grid, st);
+    return dw16 ? launch_k<NLOG2, true, true>(p, mode, grid, st) : launch_k<NLOG2, true, false>(p, mode, grid, st);
 }
 
 }  // namespace
 
 bool fast16_supported(const intfft_generics &g)
 {
-    return g.format == 0 && g.rndmode == 0 && g.use_fly == 1 && g.data_width <= 16 && g.twdl_width <= 16 &&
+    return g.format == 0 && g.use_fly == 1 && g.data_width <= 16 && g.twdl_width <= 16 &&
            g.nfft_log2 >= 8 && g.nfft_log2 <= 20;
 }
 
 // top-bits pass of an NFFT >= 13 plan: kp.g in {4, 8}, kp.pb = NFFT - kp.g
-int launch_fast16_strided(const PassDesc &pd, bool dit, const int2 *twp, int num_sms, void *stream)
+int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *twp, int num_sms, void *stream)
 {
     Strided16Params p{};
     p.in = reinterpret_cast<const uint32_t *>(pd.kp.in);
@@ -511,11 +549,11 @@ int launch_fast16_strided(const PassDesc &pd, bool dit, const int2 *twp, int num
     const bool dw16 = p.dw == 16;
     cudaError_t e;
     if (G == 4) {
-        if (!dit) e = dw16 ? launch_strided_k<4, false, true>(p, (int)grid, st) : launch_strided_k<4, false, false>(p, (int)grid, st);
-        else e = dw16 ? launch_strided_k<4, true, true>(p, (int)grid, st) : launch_strided_k<4, true, false>(p, (int)grid, st);
+        if (!dit) e = dw16 ? launch_strided_k<4, false, true>(p, mode, (int)grid, st) : launch_strided_k<4, false, false>(p, mode, (int)grid, st);
+        else e = dw16 ? launch_strided_k<4, true, true>(p, mode, (int)grid, st) : launch_strided_k<4, true, false>(p, mode, (int)grid, st);
     } else if (G == 8) {
-        if (!dit) e = dw16 ? launch_strided_k<8, false, true>(p, (int)grid, st) : launch_strided_k<8, false, false>(p, (int)grid, st);
-        else e = dw16 ? launch_strided_k<8, true, true>(p, (int)grid, st) : launch_strided_k<8, true, false>(p, (int)grid, st);
+        if (!dit) e = dw16 ? launch_strided_k<8, false, true>(p, mode, (int)grid, st) : launch_strided_k<8, false, false>(p, mode, (int)grid, st);
+        else e = dw16 ? launch_strided_k<8, true, true>(p, mode, (int)grid, st) : launch_strided_k<8, true, false>(p, mode, (int)grid, st);
     } else {
         e = cudaErrorInvalidValue;
     }
@@ -526,7 +564,6 @@ int launch_fast16_strided(const PassDesc &pd, bool dit, const int2 *twp, int num
 int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
                   int num_sms, void *stream)
 {
-    (void)mode;
     Fast16Params p{};
     p.in = reinterpret_cast<const uint32_t *>(pd.kp.in);
     p.out = reinterpret_cast<uint32_t *>(pd.kp.out);
@@ -544,11 +581,11 @@ int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const
     const bool dw16 = p.dw == 16;
     cudaError_t e;
     switch (pd.kp.g) {          // stage bits of this (contiguous) pass; == NFFT for single-pass plans
-    case 8: e = launch_n<8>(p, dit, dw16, (int)grid, st); break;
-    case 9: e = launch_n<9>(p, dit, dw16, (int)grid, st); break;
-    case 10: e = launch_n<10>(p, dit, dw16, (int)grid, st); break;
-    case 11: e = launch_n<11>(p, dit, dw16, (int)grid, st); break;
-    case 12: e = launch_n<12>(p, dit, dw16, (int)grid, st); break;
+    case 8: e = launch_n<8>(p, mode, dit, dw16, (int)grid, st); break;
+    case 9: e = launch_n<9>(p, mode, dit, dw16, (int)grid, st); break;
+    case 10: e = launch_n<10>(p, mode, dit, dw16, (int)grid, st); break;
+    case 11: e = launch_n<11>(p, mode, dit, dw16, (int)grid, st); break;
+    case 12: e = launch_n<12>(p, mode, dit, dw16, (int)grid, st); break;
     default: e = cudaErrorInvalidValue; break;
     }
     count_launch();

@@ -44,6 +44,7 @@ struct Fast32Params {
 __host__ __device__ constexpr unsigned phys8(unsigned i) { return i + 2u * (i >> 4); }
 constexpr unsigned kTile8 = 4608;
 constexpr unsigned kHead32 = 128 + 15 * 16 * 8;
+constexpr unsigned kStage32 = 16 * 256 * 8;   // prefetch staging: 16 slots x 256 threads x 8 bytes
 
 // one scalar of a sample: the value and (TRUNCATE only; dead code elsewhere) its floor-half, which is
 // all a TRUNCATE butterfly ever reads (inputs sliced (DTW-1 downto 1), int_dif2_fly.vhd:150-153)
@@ -180,6 +181,32 @@ __device__ __forceinline__ void fly32(const Stg &st, bool odd, const CmultConsts
     }
 }
 
+// ---- per-thread prefetch of the NEXT tile's first-round samples (cp.async into thread-private slots of
+// ---- a 32 KB staging area: slot [m][tid]); no barrier is involved because a thread only ever reads the
+// ---- slots it filled itself, and one staging buffer is enough because the slots are drained into
+// ---- registers at the top of a tile before the copies for the following tile are issued
+__device__ __forceinline__ void cp_async_elem(void *smem_dst, const void *gsrc, int bytes)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void stage_read(const unsigned char *stage, unsigned tid, int m, int sb, int &re, int &im)
+{
+    if (sb == 2) {
+        const unsigned x = reinterpret_cast<const unsigned *>(stage)[m * 256 + tid];
+        re = (int)(short)(x & 0xffffu);
+        im = (int)x >> 16;
+    } else {
+        const int2 v = reinterpret_cast<const int2 *>(stage)[m * 256 + tid];
+        re = v.x;
+        im = v.y;
+    }
+}
+
 struct TwRegs32 {
     const int (&r)[15];
     const int (&i)[15];
@@ -246,9 +273,31 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);                  // [15][1 << R0]
     int2(*work)[kTile8] = reinterpret_cast<int2(*)[kTile8]>(smem_raw + kHead32);
+    unsigned char *stage = smem_raw + kHead32 + 2 * kTile8 * 8;
 
     const unsigned tid = threadIdx.x;
     const bool tid_odd = tid & 1u;
+    const int esz = 2 * p.in_sb;                                             // bytes per complex sample read
+
+    // first-round ownership (the same for every tile): local index of register m
+    constexpr int RF = DIT ? 0 : NR - 1;                                      // first round processed
+    constexpr int LOF = RF == 0 ? 0 : R0 + 4 * (RF - 1);
+    constexpr int RRF = RF == 0 ? R0 : 4;
+    const unsigned basef = (tid & ((1u << LOF) - 1u)) | ((tid >> LOF) << (LOF + RRF));
+    auto prefetch = [&](long long t) {
+        const char *src = reinterpret_cast<const char *>(p.in) + ((t << 12) + basef) * esz;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const unsigned off = ((unsigned)(m & ((1 << RRF) - 1)) << LOF) | ((unsigned)(m >> RRF) << (8 + RRF));
+            cp_async_elem(stage + (m * 256 + tid) * esz, src + (long long)off * esz, esz);
+        }
+        cp_async_commit();
+    };
+    bool staged = false;
+    if ((long long)blockIdx.x < p.n_tiles && (((long long)blockIdx.x + 1) << 12) <= p.total) {
+        prefetch(blockIdx.x);
+        staged = true;
+    }
 
     // ---- batch-invariant twiddles: round 1 -> shared table, round 2 -> registers ----
     for (unsigned e = tid; e < 15u << R0; e += 256) {
@@ -290,16 +339,19 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
             const unsigned base = (tid & ((1u << lo) - 1u)) | ((tid >> lo) << (lo + R));
             const unsigned pbase = phys8(base);
 
-            if (first && full) {                      // whole tile inside the batch: no per-sample guards
+            if (first && staged) {                    // this tile was prefetched into the thread's slots
+                cp_async_wait_all();
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
-                    const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
                     int a, b;
-                    ld_sample(p.in, g0 + base + off, p.in_sb, a, b);
+                    stage_read(stage, tid, m, p.in_sb, a, b);
                     if (p.in_wrap) { a = sx(a, p.dw); b = sx(b, p.dw); }
                     re[m] = mk(a);
                     im[m] = mk(b);
                 }
+                const long long nt = tile + gridDim.x;    // refill the slots with this CTA's next tile
+                staged = nt < p.n_tiles && ((nt + 1) << 12) <= p.total;
+                if (staged) prefetch(nt);
             } else {
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
@@ -360,8 +412,10 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_kernel(const __grid_con
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);
     int2(*work)[kTile8] = reinterpret_cast<int2(*)[kTile8]>(smem_raw + kHead32);
+    unsigned char *stage = smem_raw + kHead32 + 2 * kTile8 * 8;
 
     const unsigned tid = threadIdx.x;
+    const int esz = 2 * p.in_sb;
     const int pb = p.n - G;
     const unsigned cmask = (1u << C) - 1u;
     const int mid_bits = pb - C;
@@ -396,6 +450,20 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_kernel(const __grid_con
             __syncthreads();
         }
 
+        // first-round ownership inside the 2^G x 2^C tile, and the prefetch of one frame's column block
+        constexpr int LOF = DIT ? 12 - 4 * NR : 8;
+        const unsigned basef = (tid & ((1u << LOF) - 1u)) | ((tid >> LOF) << (LOF + 4));
+        auto prefetch = [&](long long f) {
+            const char *src = reinterpret_cast<const char *>(p.in) + ((f << p.n) + ((long long)mid << C)) * esz;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const unsigned l = basef | ((unsigned)m << LOF);
+                cp_async_elem(stage + (m * 256 + tid) * esz, src + ((long long)(l >> C) * row_stride + (l & cmask)) * esz, esz);
+            }
+            cp_async_commit();
+        };
+        if (f0 < f1) prefetch(f0);
+
         for (long long f = f0; f < f1; ++f, ++it) {
             int2 *sm = work[it & 1];
             const long long gbase = (f << p.n) + ((long long)mid << C);
@@ -409,10 +477,10 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_kernel(const __grid_con
                 const unsigned pbase = phys8(base);
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
-                    const unsigned l = base | ((unsigned)m << lo);
                     int a, b;
                     if (first) {
-                        ld_sample(p.in, gbase + (long long)(l >> C) * row_stride + (l & cmask), p.in_sb, a, b);
+                        if (m == 0) cp_async_wait_all();
+                        stage_read(stage, tid, m, p.in_sb, a, b);
                         if (p.in_wrap) { a = sx(a, p.dw); b = sx(b, p.dw); }
                     } else {
                         const int2 v = sm[pbase + phys8((unsigned)m << lo)];
@@ -422,6 +490,7 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_kernel(const __grid_con
                     re[m] = mk(a);
                     im[m] = mk(b);
                 }
+                if (first && f + 1 < f1) prefetch(f + 1);
                 if (lo == 8) round32<4, DIT, MODE, KIND>(re, im, p, pb + 8 - C, TwRegs32{uwr, uwi}, false, false);
                 else round32<4, DIT, MODE, KIND>(re, im, p, pb + 4 - C, TwSmem32{midtw + (tid & 15u), 16}, false, false);
 #pragma unroll
@@ -439,7 +508,7 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_kernel(const __grid_con
 
 template <typename K> cudaError_t launch_any(K k, const Fast32Params &p, int grid, cudaStream_t st)
 {
-    const int smem = kHead32 + 2 * kTile8 * 8;
+    const int smem = kHead32 + 2 * kTile8 * 8 + kStage32;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, smem, st>>>(p);

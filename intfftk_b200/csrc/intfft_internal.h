@@ -83,7 +83,7 @@ int launch_tile_pass(const PassDesc &pd, int mode, bool dit, int num_sms, void *
 int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
                   int num_sms, void *stream);
 bool fast16_supported(const intfft_generics &g);
-int launch_fast16_strided(const PassDesc &pd, bool dit, const int2 *twp, int num_sms, void *stream);
+int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *twp, int num_sms, void *stream);
 bool fast32_supported(const intfft_generics &g);
 int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
                   int num_sms, void *stream);

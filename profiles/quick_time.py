@@ -44,6 +44,9 @@ def others():
     time_plan(65536, steps=5, NFFT=12, DATA_WIDTH=16, FORMAT=0, RNDMODE=1)
     time_plan(65536, steps=5, NFFT=12, DATA_WIDTH=16, FORMAT=1)
 
+def r12():
+    time_plan(65536, steps=3, NFFT=12, DATA_WIDTH=16, FORMAT=0, RNDMODE=1)
+
 if __name__ == "__main__":
     for name in (sys.argv[1:] or ["c2"]):
         globals()[name]()
