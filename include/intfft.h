@@ -109,6 +109,12 @@ int intfft_pair_destroy(intfft_pair *p);
 int intfft_pair_query(const intfft_pair *p, intfft_layout *l);
 int intfft_pair_exec(intfft_pair *p, const void *d_in, void *d_out, void *cuda_stream);
 
+/* f1: int_fft_single_path semantics — natural order in AND out
+ * (main/int_fft_single_path.vhd:157-268: inbuf_half_path -> int_fftNk -> outbuf_half_path -> int_bitrev_order).
+ * FFT plans: exec, then the bit-reversal reorder; IFFT plans: reorder, then exec.  d_in != d_out.
+ * The plan owns the intermediate buffer (allocated on first use). */
+int intfft_exec_natural(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream);
+
 /* f1: bit-reversal reorder of a batch of frames, the job int_bitrev_order does in
  * int_fft_single_path (buffers/int_bitrev_order.vhd:82-104): out[bitrev(q)] = in[q].
  * scalar_bytes in {2,4,8}; d_in != d_out. */

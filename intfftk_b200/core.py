@@ -55,6 +55,7 @@ def lib() -> ctypes.CDLL:
         L.intfft_query.argtypes = [vp, P(_CLayout)]
         L.intfft_exec.argtypes = [vp, vp, vp, vp]
         L.intfft_exec_host.argtypes = [vp, vp, vp]
+        L.intfft_exec_natural.argtypes = [vp, vp, vp, vp]
         L.intfft_twiddles.argtypes = [P(_CGenerics), ctypes.c_int, vp, vp]
         L.intfft_pair_create.argtypes = [P(vp), P(_CGenerics), ctypes.c_int, ctypes.c_int64, ctypes.c_int]
         L.intfft_pair_destroy.argtypes = [vp]
@@ -187,6 +188,18 @@ class Core:
         st = lib().intfft_exec(self._h, d_in.data_ptr(), d_out.data_ptr(), s)
         if st:
             raise IntfftError(st, "intfft_exec")
+        return d_out
+
+    def exec_natural(self, d_in, d_out=None, stream=None):
+        """int_fft_single_path semantics: natural order in and out (exec + int_bitrev_order)."""
+        import torch
+        if d_out is None:
+            d_out = self.new_output()
+        assert d_in.is_cuda and d_in.is_contiguous() and d_in.data_ptr() != d_out.data_ptr()
+        s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        st = lib().intfft_exec_natural(self._h, d_in.data_ptr(), d_out.data_ptr(), s)
+        if st:
+            raise IntfftError(st, "intfft_exec_natural")
         return d_out
 
     # -- host path: what a testbench-style caller uses ------------------------------------------

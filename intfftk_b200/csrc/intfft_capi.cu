@@ -121,7 +121,12 @@ void build_passes(Plan &pl)
         pd.threads = 1 << (kp.L - 4);
         pd.smem_bytes = ((size_t)1 << kp.L) * (pd.lane == LANE_I32_P64 ? 8 : 16);
         pd.scratch_in = pd.scratch_out = -1;
-        pd.path = f16 ? 1 : (f32 ? 2 : 0);
+        // a pass of a wide plan can still run on the 32-bit-lane kernels when its own widths fit them
+        // (c3: the strided top pass works on 24..28 bits, only the contiguous pass needs 64-bit lanes)
+        const bool geom32 = sp.strided ? (sp.bits == 4 || sp.bits == 8) : (sp.bits >= 8 && sp.bits <= 12);
+        const bool span32 = !no_fast && g.use_fly && geom32 && kp.L == 12 && (w_out + rnd_extra) <= 32 &&
+                            kp.in_sb <= 4 && kp.out_sb <= 4;
+        pd.path = f16 ? 1 : ((f32 || span32) ? 2 : 0);
         stages_done += sp.bits;
         pl.passes.push_back(pd);
     }
@@ -232,6 +237,7 @@ int intfft_plan_destroy(intfft_plan *p)
     cudaFree(p->scratch[1]);
     cudaFree(p->h2d);
     cudaFree(p->d2h);
+    cudaFree(p->nat);
     for (void *e : p->ev_in) cudaEventDestroy((cudaEvent_t)e);
     for (void *e : p->ev_k) cudaEventDestroy((cudaEvent_t)e);
     if (p->s_in) { cudaStreamDestroy((cudaStream_t)p->s_in); cudaStreamDestroy((cudaStream_t)p->s_k); cudaStreamDestroy((cudaStream_t)p->s_out); }
@@ -295,6 +301,27 @@ int intfft_exec(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream
     DeviceGuard guard(p->device);
     if (!guard.ok) return INTFFT_ECUDA;
     return exec_frames(p, d_in, d_out, p->batch, cuda_stream);
+}
+
+int intfft_exec_natural(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream)
+{
+    if (!p || !d_in || !d_out || d_in == d_out) return INTFFT_EINVAL;
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return INTFFT_ECUDA;
+    intfft_layout l;
+    intfft_query(p, &l);
+    const bool dit = p->g.direction != 0;
+    // the reorder acts on the bit-reversed side: the FFT's output / the IFFT's input
+    const size_t need = (size_t)(dit ? l.in_bytes : l.out_bytes);
+    if (!p->nat && cudaMalloc(&p->nat, need) != cudaSuccess) return INTFFT_ENOMEM;
+    const int n = p->g.nfft_log2;
+    if (!dit) {
+        const int st = exec_frames(p, d_in, p->nat, p->batch, cuda_stream);
+        if (st) return st;
+        return launch_bitrev(n, p->out_sb, p->batch, p->nat, d_out, cuda_stream) ? INTFFT_ECUDA : INTFFT_OK;
+    }
+    if (launch_bitrev(n, p->in_sb, p->batch, d_in, p->nat, cuda_stream)) return INTFFT_ECUDA;
+    return exec_frames(p, p->nat, d_out, p->batch, cuda_stream);
 }
 
 // Host buffers: the batch is cut into chunks that flow through three streams (H2D copy, kernels,

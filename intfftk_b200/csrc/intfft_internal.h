@@ -73,6 +73,7 @@ struct Plan {
     void *scratch[2] = {nullptr, nullptr};
     size_t scratch_bytes[2] = {0, 0};
     void *h2d = nullptr, *d2h = nullptr;  // device staging for intfft_exec_host
+    void *nat = nullptr;                  // bit-reversed intermediate of intfft_exec_natural
     void *s_in = nullptr, *s_k = nullptr, *s_out = nullptr;   // cudaStream_t: H2D / kernels / D2H pipeline
     std::vector<void *> ev_in, ev_k;                          // cudaEvent_t per chunk
     int num_sms = 0;

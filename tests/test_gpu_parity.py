@@ -254,6 +254,35 @@ def test_cpp_host_replays_testbench_files(ib, oracle, tmp_path):
     assert np.array_equal(got[..., 2], fin[:, : n // 2, 1]) and np.array_equal(got[..., 3], fin[:, n // 2:, 1])
 
 
+@pytest.mark.parametrize("kw", [dict(NFFT=7, DATA_WIDTH=16, FORMAT=1), dict(NFFT=12, DATA_WIDTH=16, FORMAT=0),
+                                dict(NFFT=13, DATA_WIDTH=18, FORMAT=0), dict(NFFT=16, DATA_WIDTH=24, FORMAT=1)])
+def test_single_path_natural_order(ib, oracle, kw):
+    """f1: int_fft_single_path = core + int_bitrev_order: natural order in and out, both directions; the
+    scaled forward result must also sit within a few LSB of numpy's fft / N at natural bin positions."""
+    g = ib.Generics(**kw)
+    n, batch = 1 << g.NFFT, 3
+    x = oracle.fill_random(batch * n * 2, g.DATA_WIDTH - 1, 3).reshape(batch, n, 2).astype(oracle.scalar_dtype(g.DATA_WIDTH))
+    og = oracle.generics(g.NFFT, g.DATA_WIDTH, g.TWDL_WIDTH, g.FORMAT, g.RNDMODE, 1, 1, 0)
+    fwd = ib.Core(g, batch, 0)
+    got = fwd.exec_natural(torch.from_numpy(x).cuda()).cpu().numpy()
+    want = oracle.bitrev(g.NFFT, oracle.batch(og, x))
+    assert np.array_equal(got, want)
+    if g.FORMAT == 0:
+        ref = np.fft.fft(x[..., 0].astype(np.float64) + 1j * x[..., 1], axis=1) / n
+        assert np.abs((got[..., 0] + 1j * got[..., 1]) - ref).max() < 16.0
+    # inverse core on a natural-order spectrum
+    gi = ib.Generics(**dict(kw, DATA_WIDTH=g.out_width)) if g.FORMAT == 0 or g.out_width + g.NFFT <= 64 else None
+    if gi is not None and ib.validate(gi, 1) == 0:
+        inv = ib.Core(gi, batch, 1)
+        spec = want                                   # natural-order spectrum
+        got_i = inv.exec_natural(torch.from_numpy(spec).cuda()).cpu().numpy()
+        ogi = oracle.generics(gi.NFFT, gi.DATA_WIDTH, gi.TWDL_WIDTH, gi.FORMAT, gi.RNDMODE, 1, 1, 1)
+        want_i = oracle.batch(ogi, oracle.bitrev(g.NFFT, spec))
+        assert np.array_equal(got_i, want_i)
+        inv.close()
+    fwd.close()
+
+
 def test_use_fly_bypass(ib, oracle):
     for fmt in (0, 1):
         got, want = _run_both(ib, oracle, 5, seed=3, NFFT=9, DATA_WIDTH=12, FORMAT=fmt, USE_FLY=0)
