@@ -80,7 +80,22 @@ void build_passes(Plan &pl)
     const bool no_fast = std::getenv("INTFFT_DISABLE_FAST16") != nullptr;   // tests: force the generic kernel
     const bool f16 = !no_fast && g.use_fly && fast16_supported(g);
     const bool f32 = !no_fast && !f16 && fast32_supported(g);
-    if ((f16 || f32) && n >= 13) {
+    // wide plans (some stage beyond 32 bits): STAGE 7..0 on the 64-bit-lane warp-centric kernel, the
+    // n - 8 stage bits above them as one strided pass (c3: 8 strided bits on 32-bit lanes + 8 here)
+    bool wide8 = false;
+    if (!no_fast && g.use_fly && !f16 && !f32 && (n == 8 || (n >= 12 && n <= 16))) {
+        const int before = dit ? 0 : n - 8;
+        const int w_out = g.data_width + (before + 8) * g.format;
+        const int max_dtwc = dit ? (w_out - g.format) : w_out;
+        PassParams t{};
+        t.n = n; t.dw = g.data_width; t.format = g.format; t.cm = cm;
+        wide8 = pick_lane(w_out + rnd_extra, max_dtwc, g.twdl_width) == LANE_I64_P64 && fast64_uniform_kind(t, dit) >= 0;
+    }
+    if (wide8) {
+        if (n == 8) spans.push_back({0, 8, false});
+        else if (!dit) { spans.push_back({8, n - 8, true}); spans.push_back({0, 8, false}); }
+        else           { spans.push_back({0, 8, false}); spans.push_back({8, n - 8, true}); }
+    } else if ((f16 || f32) && n >= 13) {
         // packed-16 kernels: top 4 or 8 bits as a strided pass, the rest (9..12 bits) contiguous
         const int g_hi = n <= 16 ? 4 : 8, g_lo = n - g_hi;
         if (!dit) { spans.push_back({g_lo, g_hi, true}); spans.push_back({0, g_lo, false}); }
@@ -100,7 +115,7 @@ void build_passes(Plan &pl)
         PassDesc pd{};
         PassParams &kp = pd.kp;
         kp.n = n;
-        kp.L = (!f16 && !f32 && !sp.strided && n == 13) ? 13 : 12;
+        kp.L = (!f16 && !f32 && !wide8 && !sp.strided && n == 13) ? 13 : 12;
         kp.g = sp.bits;
         kp.pb = sp.lo_bit;
         kp.c = sp.strided ? kp.L - sp.bits : 0;
@@ -127,6 +142,7 @@ void build_passes(Plan &pl)
         const bool span32 = !no_fast && g.use_fly && geom32 && kp.L == 12 && (w_out + rnd_extra) <= 32 &&
                             kp.in_sb <= 4 && kp.out_sb <= 4;
         pd.path = f16 ? 1 : ((f32 || span32) ? 2 : 0);
+        if (wide8 && !sp.strided) pd.path = 3;
         stages_done += sp.bits;
         pl.passes.push_back(pd);
     }
@@ -287,6 +303,8 @@ static int exec_frames(intfft_plan *p, const void *d_in, void *d_out, long long 
                             : launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream);
         else if (pd.path == 2)
             e = launch_fast32(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
+        else if (pd.path == 3)
+            e = launch_fast64(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
         else
             e = launch_tile_pass(pd, p->mode, dit, p->num_sms, cuda_stream);
         if (e) return INTFFT_ECUDA;

@@ -1,0 +1,384 @@
+// 64-bit-lane stage-chain kernel for the lowest eight stage bits (STAGE 7 .. 0) of plans whose values
+// outgrow 32 bits: BASELINE c3 (65536-pt, 24-bit UNSCALED: widths 24 -> 40) runs its first eight
+// stages on the 32-bit-lane strided kernel (intfft_fast32.cuh) and its last eight here.
+//
+// Reference rules implemented (paths relative to the reference root):
+//   src/vhdl/fft/int_dif2_fly.vhd:142-373, src/vhdl/fft/int_dit2_fly.vhd:140-325      butterflies
+//   src/vhdl/math/cmult/int_cmult_dsp48.vhd:182-190 / 307-317                          single DSP48 pair
+//   src/vhdl/math/cmult/int_cmult_dbl18_dsp48.vhd:163-181, int_cmult_dbl35_dsp48.vhd:155-168   double
+//   src/vhdl/math/cmult/int_cmult_trpl18_dsp48.vhd:151-155, int_cmult_trpl52_dsp48.vhd:150-170 triple
+// The double arrangement's 48-bit wrap is not materialised: the kept slice ends at bit
+// sh_post + dtwc - 1 <= 46 (dtwc < 45 / 43 with sh_post = 3 / 5; dtwc < 36 with sh_post = 12).
+//
+// Shape: 256 contiguous samples are an independent sub-transform of these eight stages, so the kernel
+// is warp-centric and has NO CTA barrier: a warp owns 512 samples (two sub-blocks, one per half-warp),
+// a thread keeps 16 samples in registers for four stages, and the single ownership change
+// (stride-16 <-> 16 contiguous) goes through a warp-private, skewed shared-memory tile under
+// __syncwarp.  Twiddles of STAGE 4..7 depend only on lane & 15 -> hoisted into registers for the whole
+// persistent loop; those of STAGE 2, 3 are kernel parameters (constant bank).
+// Products are exact 64-bit: D = hi' * 2^32 + (signed) lo, D * W = mul.wide.s32(lo, W) + ((hi' * W) << 32).
+#include <cuda_runtime.h>
+
+#include "intfft_arith.cuh"
+
+namespace intfft {
+
+namespace {
+
+struct Fast64Params {
+    const void *in;
+    void *out;
+    const int2 *tw;          // raw twiddles, entry (1 << s) + k
+    int64_t total;         // frames * N samples (a multiple of 256)
+    int64_t n_chunks;      // chunks of 512 samples (the last one may hold a single sub-block)
+    int n;                   // NFFT of the whole transform
+    int dw, format;
+    int in_sb, out_sb;       // scalar bytes of the containers read / written
+    int in_wrap;
+    CmultConsts cm;
+    int lw_r[16], lw_i[16];  // STAGE 2, 3 twiddles, index (1 << s) - 1 + k
+};
+
+constexpr int kWarpSlots = 544;      // 512 samples + one 16-byte slot of skew per 16 samples
+
+// sample index inside a warp's 512-sample chunk -> 16-byte slot; additive for disjoint bit sets
+__host__ __device__ constexpr unsigned phys64(unsigned i) { return i + (i >> 4); }
+
+struct Stg64 {
+    int s, ow, dtwc;
+};
+template <bool DIT, int MODE> __device__ __forceinline__ Stg64 stage64(const Fast64Params &p, int s)
+{
+    constexpr int FORMAT = MODE == MODE_UNSCALED ? 1 : 0;
+    Stg64 st;
+    st.s = s;
+    const int ii = DIT ? s : p.n - 1 - s;
+    const int dtw = p.dw + ii * FORMAT;
+    st.ow = dtw + FORMAT;
+    st.dtwc = DIT ? dtw : st.ow;
+    return st;
+}
+
+__device__ __forceinline__ unsigned lo32(int64_t v) { return (unsigned)v; }
+__device__ __forceinline__ int hi32(int64_t v) { return (int)(v >> 32); }
+__device__ __forceinline__ int64_t mk64(unsigned lo, int hi) { return (int64_t)(((uint64_t)(unsigned)hi << 32) | lo); }
+
+// d = hi * 2^32 + (int)lo with hi corrected for the sign of the low word
+struct Split {
+    int lo, hi;
+};
+__device__ __forceinline__ Split split64(int64_t d)
+{
+    Split r;
+    r.lo = (int)lo32(d);
+    r.hi = hi32(d) + (int)((unsigned)r.lo >> 31);
+    return r;
+}
+// exact signed 32 x 32 -> 64 (asm: the front end otherwise widens both operands and emits a 64 x 64 multiply)
+__device__ __forceinline__ int64_t mulw(int a, int b)
+{
+    int64_t r;
+    asm("mul.wide.s32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ int64_t madw(int a, int b, int64_t c)
+{
+    int64_t r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
+// acc + d * w (low 64 bits, exact when the true value fits): IMAD.WIDE + IMAD
+__device__ __forceinline__ int64_t mad64x32(const Split &d, int w, int64_t acc)
+{
+    const int64_t t = madw(d.lo, w, acc);
+    return mk64(lo32(t), hi32(t) + d.hi * w);
+}
+__device__ __forceinline__ int64_t mul64x32(const Split &d, int w)
+{
+    const int64_t t = mulw(d.lo, w);
+    return mk64(lo32(t), hi32(t) + d.hi * w);
+}
+
+// t >> sh, 0 <= sh < 32 (every pre / post shift of the multiplier arrangements is below 32)
+__device__ __forceinline__ int64_t sra64(int64_t t, int sh)
+{
+    return mk64(__funnelshift_r(lo32(t), (unsigned)hi32(t), sh), hi32(t) >> sh);
+}
+// keep the low w bits of v, sign-extended, 32 < w <= 64
+__device__ __forceinline__ int64_t wrap_hi(int64_t v, int w)
+{
+    return mk64(lo32(v), (int)((unsigned)hi32(v) << (64 - w)) >> (64 - w));
+}
+// bits [sh + w - 1 : sh] of t, sign-extended; 0 <= sh < 32 < w, sh + w <= 64 (all grid-uniform)
+__device__ __forceinline__ int64_t field64(int64_t t, int sh, int w)
+{
+    return mk64(__funnelshift_r(lo32(t), (unsigned)hi32(t), sh), (int)((unsigned)hi32(t) << (64 - sh - w)) >> (64 - w));
+}
+
+// KIND: 0 single, 1 double, 2 triple (the same for every multiplying stage of the pass)
+template <int KIND>
+__device__ __forceinline__ void cmul64(int64_t dr, int64_t di, int wr, int wi, const CmultConsts &cm, int dtwc,
+                                       int64_t &o_re, int64_t &o_im)
+{
+    const Split r = split64(dr), i = split64(di);
+    if (KIND == 0) {
+        const int64_t tr = mad64x32(i, -wi, mul64x32(r, wr));
+        const int64_t ti = mad64x32(i, wr, mul64x32(r, wi));
+        o_re = field64(tr, cm.sh_single, dtwc);
+        o_im = field64(ti, cm.sh_single, dtwc);
+    } else if (KIND == 1) {
+        const int64_t tr = sra64(mul64x32(r, wr), cm.k_pre) - sra64(mul64x32(i, wi), cm.k_pre);
+        const int64_t ti = sra64(mul64x32(r, wi), cm.k_pre) + sra64(mul64x32(i, wr), cm.k_pre);
+        o_re = field64(tr, cm.sh_post, dtwc);
+        o_im = field64(ti, cm.sh_post, dtwc);
+    } else {
+        const int64_t a = field64(mul64x32(r, wr), cm.sh_single, dtwc), b = field64(mul64x32(i, wi), cm.sh_single, dtwc);
+        const int64_t c = field64(mul64x32(r, wi), cm.sh_single, dtwc), d = field64(mul64x32(i, wr), cm.sh_single, dtwc);
+        o_re = wrap_hi((int64_t)((uint64_t)a - (uint64_t)b), dtwc);
+        o_im = wrap_hi((int64_t)((uint64_t)c + (uint64_t)d), dtwc);
+    }
+}
+
+// -v for v >= 0, ~v for v < 0; the result always fits the operand's width
+__device__ __forceinline__ int64_t negq64(int64_t v) { return (v >> 63) - v; }
+
+// `ow` > 32: only the ROUNDING difference can leave it (see addsub<> in intfft_arith.cuh)
+template <int MODE> __device__ __forceinline__ void addsub64(int64_t a, int64_t b, int ow, int64_t &ad, int64_t &su)
+{
+    if (MODE == MODE_TRUNC) {
+        const int64_t ha = sra64(a, 1), hb = sra64(b, 1);
+        ad = ha + hb;
+        su = ha - hb;
+    } else if (MODE == MODE_ROUND) {
+        const int64_t s = (int64_t)((uint64_t)a + (uint64_t)b + 1u), d = (int64_t)((uint64_t)a - (uint64_t)b + 1u);
+        ad = sra64(s, 1);
+        su = wrap_hi(sra64(d, 1), ow);
+    } else {
+        ad = (int64_t)((uint64_t)a + (uint64_t)b);
+        su = (int64_t)((uint64_t)a - (uint64_t)b);
+    }
+}
+
+template <bool DIT, int MODE, int KIND>
+__device__ __forceinline__ void fly64(const Stg64 &st, bool odd, const CmultConsts &cm, int64_t &ar, int64_t &ai,
+                                      int64_t &br, int64_t &bi, int wr, int wi)
+{
+    using T = int64_t;
+    if (!DIT) {
+        T xr, xi, sr, si;
+        addsub64<MODE>(ar, br, st.ow, xr, sr);
+        addsub64<MODE>(ai, bi, st.ow, xi, si);
+        ar = xr;
+        ai = xi;
+        if (st.s == 0) {
+            br = sr;
+            bi = si;
+        } else if (st.s == 1) {
+            br = odd ? si : sr;
+            bi = odd ? negq64(sr) : si;
+        } else {
+            cmul64<KIND>(sr, si, wr, wi, cm, st.dtwc, br, bi);
+        }
+    } else {
+        T wr_, wi_;
+        if (st.s == 0) {
+            wr_ = br;
+            wi_ = bi;
+        } else if (st.s == 1) {
+            wr_ = odd ? negq64(bi) : br;
+            wi_ = odd ? br : bi;
+        } else {                                      // multiplier fed with swapped re / im, outputs swapped back
+            T o_re, o_im;
+            cmul64<KIND>(bi, br, wr, wi, cm, st.dtwc, o_re, o_im);
+            wi_ = o_re;
+            wr_ = o_im;
+        }
+        T xr, xi, yr, yi;
+        addsub64<MODE>(ar, wr_, st.ow, xr, yr);
+        addsub64<MODE>(ai, wi_, st.ow, xi, yi);
+        ar = xr; ai = xi;
+        br = yr; bi = yi;
+    }
+}
+
+// four stages (global STAGE S0 .. S0+3) on the register index bits 0..3
+template <int S0, bool DIT, int MODE, int KIND>
+__device__ __forceinline__ void round64(int64_t (&re)[16], int64_t (&im)[16], const Fast64Params &p,
+                                        const int (&twr)[15], const int (&twi)[15])
+{
+#pragma unroll
+    for (int step = 0; step < 4; ++step) {
+        const int q = DIT ? step : 3 - step;
+        const Stg64 st = stage64<DIT, MODE>(p, S0 + q);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            if (m & (1 << q)) continue;
+            const int w = (1 << q) - 1 + (m & ((1 << q) - 1));
+            int wr = 0, wi = 0;
+            if (S0 + q >= 2) { wr = twr[w]; wi = twi[w]; }
+            fly64<DIT, MODE, KIND>(st, (m & 1) != 0, p.cm, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi);
+        }
+    }
+}
+
+template <bool DIT, int MODE, int KIND>
+__global__ void __launch_bounds__(256, 2) fast64_kernel(const __grid_constant__ Fast64Params p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    longlong2 *sm = reinterpret_cast<longlong2 *>(smem_raw) + warp * kWarpSlots;
+    const unsigned sub = lane >> 4, l4 = lane & 15u;
+
+    // STAGE 4..7 twiddles: index = (position mod 2^s) = l4 + 16 * j
+    int uwr[15], uwi[15];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < (1 << q); ++j) {
+            const int2 w = __ldg(p.tw + (1u << (4 + q)) + l4 + ((unsigned)j << 4));
+            uwr[(1 << q) - 1 + j] = w.x;
+            uwi[(1 << q) - 1 + j] = w.y;
+        }
+    int lwr[15], lwi[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) { lwr[i] = p.lw_r[i]; lwi[i] = p.lw_i[i]; }
+
+    // layouts inside the chunk: A = stride-16 ownership (register bits = sample bits 4..7),
+    //                           B = 16 contiguous samples  (register bits = sample bits 0..3)
+    const unsigned baseA = sub * 256u + l4, baseB = sub * 256u + 16u * l4;
+    const unsigned pA = phys64(baseA), pB = phys64(baseB);
+
+    for (int64_t chunk = (int64_t)blockIdx.x * 8 + warp; chunk < p.n_chunks; chunk += (int64_t)gridDim.x * 8) {
+        const int64_t g0 = chunk << 9;
+        const bool active = g0 + sub * 256 < p.total;
+        int64_t re[16], im[16];
+        // ---- first round: straight from HBM (container chosen outside the unrolled loop) ----
+        if (p.in_sb == 4) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                int2 v = make_int2(0, 0);
+                if (active) v = __ldg(reinterpret_cast<const int2 *>(p.in) + g0 + (DIT ? baseB + m : baseA + 16u * m));
+                re[m] = v.x;
+                im[m] = v.y;
+            }
+        } else if (p.in_sb == 8) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                longlong2 v = make_longlong2(0, 0);
+                if (active) v = __ldg(reinterpret_cast<const longlong2 *>(p.in) + g0 + (DIT ? baseB + m : baseA + 16u * m));
+                re[m] = v.x;
+                im[m] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                short2 v = make_short2(0, 0);
+                if (active) v = __ldg(reinterpret_cast<const short2 *>(p.in) + g0 + (DIT ? baseB + m : baseA + 16u * m));
+                re[m] = v.x;
+                im[m] = v.y;
+            }
+        }
+        if (p.in_wrap) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) { re[m] = wrapw<int64_t>(re[m], p.dw); im[m] = wrapw<int64_t>(im[m], p.dw); }
+        }
+        if (DIT) round64<0, DIT, MODE, KIND>(re, im, p, lwr, lwi);
+        else round64<4, DIT, MODE, KIND>(re, im, p, uwr, uwi);
+        // ---- ownership change inside the warp ----
+        __syncwarp();                                  // previous chunk's reads of the tile are complete
+#pragma unroll
+        for (int m = 0; m < 16; ++m) sm[DIT ? pB + m : pA + phys64(16u * m)] = make_longlong2(re[m], im[m]);
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const longlong2 v = sm[DIT ? pA + phys64(16u * m) : pB + m];
+            re[m] = v.x;
+            im[m] = v.y;
+        }
+        if (DIT) round64<4, DIT, MODE, KIND>(re, im, p, uwr, uwi);
+        else round64<0, DIT, MODE, KIND>(re, im, p, lwr, lwi);
+        if (active) {
+            if (p.out_sb == 8) {
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+                    reinterpret_cast<longlong2 *>(p.out)[g0 + (DIT ? baseA + 16u * m : baseB + m)] = make_longlong2(re[m], im[m]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+                    reinterpret_cast<int2 *>(p.out)[g0 + (DIT ? baseA + 16u * m : baseB + m)] = make_int2((int)re[m], (int)im[m]);
+            }
+        }
+    }
+}
+
+template <bool DIT, int MODE> cudaError_t launch_k(const Fast64Params &p, int kind, int grid, cudaStream_t st)
+{
+    using K = void (*)(const Fast64Params);
+    // KIND 0 (single DSP48 pair) needs dtwc < 28 and so never meets this kernel's "wraps above 32 bits" rule
+    if (kind != 1 && kind != 2) return cudaErrorInvalidValue;
+    K k = kind == 1 ? (K)fast64_kernel<DIT, MODE, 1> : (K)fast64_kernel<DIT, MODE, 2>;
+    const int smem = 8 * kWarpSlots * 16;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// multiplier arrangement shared by every multiplying stage (STAGE 2..7) of the pass; -1 when they differ
+// or when some stage of the pass still wraps at <= 32 bits (the kernel's slices assume a live high word)
+int fast64_uniform_kind(const PassParams &kp, bool dit)
+{
+    int kind = -1;
+    for (int s = 0; s < 8; ++s) {
+        const int ii = dit ? s : kp.n - 1 - s;
+        const int dtw = kp.dw + ii * kp.format;
+        const int dtwc = dit ? dtw : dtw + kp.format;
+        if (dtwc <= 32 || dtw + kp.format <= 32) return -1;
+        if (s < 2) continue;
+        const int k = dtwc < kp.cm.lim_single ? 0 : (dtwc < kp.cm.lim_dbl ? 1 : 2);
+        if (kind >= 0 && k != kind) return -1;
+        kind = k;
+    }
+    return kind;
+}
+
+int launch_fast64(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
+                  int num_sms, void *stream)
+{
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Fast64Params p{};
+    p.in = pd.kp.in;
+    p.out = pd.kp.out;
+    p.tw = tw;
+    p.total = pd.kp.total;
+    p.n_chunks = (pd.kp.total + 511) >> 9;
+    p.n = pd.kp.n;
+    p.dw = pd.kp.dw;
+    p.format = pd.kp.format;
+    p.in_sb = pd.kp.in_sb;
+    p.out_sb = pd.kp.out_sb;
+    p.in_wrap = pd.kp.in_wrap;
+    p.cm = pd.kp.cm;
+    for (int i = 0; i < 16; ++i) { p.lw_r[i] = lw_r[i]; p.lw_i[i] = lw_i[i]; }
+    const int kind = fast64_uniform_kind(pd.kp, dit);
+    if (kind < 0) return (int)cudaErrorInvalidValue;
+    int64_t grid = 2ll * num_sms;
+    const int64_t need = (p.n_chunks + 7) / 8;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    cudaError_t e;
+    switch (mode * 2 + (dit ? 1 : 0)) {
+    case MODE_TRUNC * 2 + 0: e = launch_k<false, MODE_TRUNC>(p, kind, (int)grid, st); break;
+    case MODE_TRUNC * 2 + 1: e = launch_k<true, MODE_TRUNC>(p, kind, (int)grid, st); break;
+    case MODE_ROUND * 2 + 0: e = launch_k<false, MODE_ROUND>(p, kind, (int)grid, st); break;
+    case MODE_ROUND * 2 + 1: e = launch_k<true, MODE_ROUND>(p, kind, (int)grid, st); break;
+    case MODE_UNSCALED * 2 + 0: e = launch_k<false, MODE_UNSCALED>(p, kind, (int)grid, st); break;
+    default: e = launch_k<true, MODE_UNSCALED>(p, kind, (int)grid, st); break;
+    }
+    count_launch();
+    return (int)e;
+}
+
+}  // namespace intfft

@@ -56,7 +56,7 @@ struct PassDesc {
     int threads;
     size_t smem_bytes;
     int scratch_in, scratch_out;  // -1 = user buffer, else index of plan scratch buffer
-    int path;              // 0 generic tile kernel, 1 packed-16 kernels, 2 32-bit-lane kernels
+    int path;              // 0 generic tile kernel, 1 packed-16 kernels, 2 32-bit-lane kernels, 3 64-bit-lane low-8 kernel
 };
 
 struct Plan {
@@ -87,6 +87,10 @@ bool fast16_supported(const intfft_generics &g);
 int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *twp, int num_sms, void *stream);
 bool fast32_supported(const intfft_generics &g);
 int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
+                  int num_sms, void *stream);
+// 64-bit-lane kernel for the lowest eight stage bits (intfft_fast64.cu)
+int fast64_uniform_kind(const PassParams &kp, bool dit);
+int launch_fast64(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
                   int num_sms, void *stream);
 int launch_bypass(const void *in, void *out, long long n_scalars, int in_sb, int out_sb, int dw,
                   int zero_extend, void *stream);

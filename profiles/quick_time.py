@@ -44,6 +44,15 @@ def others():
     time_plan(65536, steps=5, NFFT=12, DATA_WIDTH=16, FORMAT=0, RNDMODE=1)
     time_plan(65536, steps=5, NFFT=12, DATA_WIDTH=16, FORMAT=1)
 
+def c3():
+    time_plan(4096, steps=10, NFFT=16, DATA_WIDTH=24, FORMAT=1)
+
+def c5():
+    time_plan(131072, steps=10, direction=1, NFFT=13, DATA_WIDTH=18, FORMAT=0)
+
+def c4():
+    time_plan(256, steps=10, NFFT=20, DATA_WIDTH=16, FORMAT=0)
+
 def r12():
     time_plan(65536, steps=3, NFFT=12, DATA_WIDTH=16, FORMAT=0, RNDMODE=1)
 

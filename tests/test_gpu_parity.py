@@ -160,6 +160,48 @@ def test_lane32_kernels_match_generic_kernel(ib, oracle, monkeypatch):
             fast.close(); slow.close()
 
 
+LANE64 = [  # (nfft, dw, tw, xser, fmt, rnd): plans whose STAGE 7..0 run on the 64-bit-lane warp-centric kernel
+    (8, 33, 16, "NEW", 0, 0), (8, 36, 16, "OLD", 0, 1), (8, 40, 18, "NEW", 1, 0), (8, 44, 16, "NEW", 0, 0),   # dbl18
+    (8, 46, 16, "NEW", 0, 0), (8, 47, 16, "OLD", 0, 1), (8, 45, 12, "NEW", 1, 0),                             # trpl18
+    (8, 33, 24, "NEW", 0, 0), (8, 35, 27, "NEW", 0, 1), (8, 34, 19, "OLD", 0, 0),                             # dbl35
+    (8, 36, 24, "NEW", 0, 1), (8, 38, 22, "OLD", 1, 0), (8, 40, 24, "NEW", 0, 0),                             # trpl52
+    (12, 30, 16, "NEW", 1, 0), (12, 34, 16, "NEW", 1, 0), (12, 40, 16, "OLD", 0, 0), (13, 36, 16, "NEW", 0, 1),
+    (14, 33, 17, "NEW", 0, 0), (15, 26, 16, "NEW", 1, 0), (16, 24, 16, "NEW", 1, 0), (16, 24, 16, "OLD", 1, 0),
+    (16, 38, 20, "NEW", 0, 0)]
+
+
+@pytest.mark.parametrize("nfft,dw,tw,xser,fmt,rnd", LANE64)
+@pytest.mark.parametrize("direction", [0, 1])
+def test_parity_lane64_kernel(ib, oracle, nfft, dw, tw, xser, fmt, rnd, direction):
+    """64-bit-lane kernel (intfft_fast64.cu): double / triple multiplier arrangements of both TWDL_WIDTH
+    families, all three modes, both directions, ragged batches; c3's generics are the (16, 24) rows."""
+    if direction == 0 and fmt == 1 and rnd == 1:
+        pytest.skip("does not elaborate")
+    g = ib.Generics(NFFT=nfft, DATA_WIDTH=dw, TWDL_WIDTH=tw, FORMAT=fmt, RNDMODE=rnd, XSER=xser)
+    if ib.validate(g, direction) != 0:
+        pytest.skip("generics do not elaborate / exceed 64-bit lanes")
+    batch = 2 if nfft >= 12 else 7
+    got, want = _run_both(ib, oracle, batch, seed=nfft * 64 + dw, via="device", NFFT=nfft, DATA_WIDTH=dw, TWDL_WIDTH=tw,
+                          FORMAT=fmt, RNDMODE=rnd, XSER=xser, direction=direction)
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+
+
+def test_lane64_kernel_matches_generic_kernel(ib, oracle, monkeypatch):
+    for kw in (dict(NFFT=16, DATA_WIDTH=24, FORMAT=1), dict(NFFT=8, DATA_WIDTH=40, FORMAT=0), dict(NFFT=12, DATA_WIDTH=35, FORMAT=0, RNDMODE=1)):
+        g = ib.Generics(**kw)
+        n = 1 << g.NFFT
+        x = torch.from_numpy(oracle.fill_random(3 * n * 2, g.DATA_WIDTH, 5).reshape(3, n, 2)).cuda()
+        for direction in (0, 1):
+            if ib.validate(g, direction) != 0:
+                continue
+            fast = ib.Core(g, 3, direction)
+            monkeypatch.setenv("INTFFT_DISABLE_FAST16", "1")
+            slow = ib.Core(g, 3, direction)
+            monkeypatch.delenv("INTFFT_DISABLE_FAST16")
+            assert torch.equal(fast.exec(x), slow.exec(x))
+            fast.close(); slow.close()
+
+
 @pytest.mark.parametrize("xser", ["NEW", "OLD"])
 def test_parity_nfft20_taylor_extension(ib, oracle, xser):
     """BASELINE config c4 shape (one frame): 2^20 points, Taylor twiddles on STAGE 11..19."""
