@@ -95,6 +95,8 @@ void build_passes(Plan &pl)
         if (n == 8) spans.push_back({0, 8, false});
         else if (!dit) { spans.push_back({8, n - 8, true}); spans.push_back({0, 8, false}); }
         else           { spans.push_back({0, 8, false}); spans.push_back({8, n - 8, true}); }
+    } else if (f32 && n == 13 && !std::getenv("INTFFT_N13_TWO_PASS")) {
+        spans.push_back({0, 13, false});              // one-pass 8192-point kernel (intfft_fast32_n13.cu)
     } else if ((f16 || f32) && n >= 13) {
         // packed-16 kernels: top 4 or 8 bits as a strided pass, the rest (9..12 bits) contiguous
         const int g_hi = n <= 16 ? 4 : 8, g_lo = n - g_hi;
@@ -115,7 +117,7 @@ void build_passes(Plan &pl)
         PassDesc pd{};
         PassParams &kp = pd.kp;
         kp.n = n;
-        kp.L = (!f16 && !f32 && !wide8 && !sp.strided && n == 13) ? 13 : 12;
+        kp.L = (!f16 && !wide8 && !sp.strided && n == 13 && sp.bits == 13) ? 13 : 12;
         kp.g = sp.bits;
         kp.pb = sp.lo_bit;
         kp.c = sp.strided ? kp.L - sp.bits : 0;

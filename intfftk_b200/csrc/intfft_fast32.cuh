@@ -122,12 +122,17 @@ __device__ __forceinline__ void cmul32(int dr, int di, int wr, int wi, const Cmu
     }
 }
 
+// inline PTX pins the instruction selection: ptxas fuses shr + add into LEA.HI.SX32 and keeps the
+// multiply-subtract on the IMAD port (the front end would otherwise re-derive two shifts and two adds)
+__device__ __forceinline__ int sra1(int x) { int r; asm("shr.s32 %0, %1, 1;" : "=r"(r) : "r"(x)); return r; }
+__device__ __forceinline__ int msub2(int t, int x) { int r; asm("mad.lo.s32 %0, %1, -2, %2;" : "=r"(r) : "r"(t), "r"(x)); return r; }
+
 template <int MODE> __device__ __forceinline__ void addsub32(const V &a, const V &b, int ow, V &x, V &y)
 {
     int xf, yf;
-    if (MODE == MODE_TRUNC) {
-        xf = a.h + b.h;
-        yf = a.h - b.h;
+    if (MODE == MODE_TRUNC) {                   // (A>>1) + (B>>1) as one shift-add; (A>>1) - (B>>1) = sum - 2 (B>>1)
+        xf = sra1(a.f) + b.h;                   // so only the B operand's half is ever materialised
+        yf = msub2(b.h, xf);
     } else if (MODE == MODE_ROUND) {            // (v >> 1) + v(0) == (v + 1) >> 1
         xf = (int)((unsigned)a.f + (unsigned)b.f + 1u) >> 1;
         // the rounded difference can reach 2^(ow-1) and is kept in ow bits by the reference
@@ -556,5 +561,6 @@ template <int G, bool DIT> cudaError_t launch_strided(const Fast32Params &p, int
 int f32_launch_contig_dif(const f32::Fast32Params &p, int bits, int mode, int kind, int grid, void *stream);
 int f32_launch_contig_dit(const f32::Fast32Params &p, int bits, int mode, int kind, int grid, void *stream);
 int f32_launch_strided(const f32::Fast32Params &p, int g, bool dit, int mode, int kind, int grid, void *stream);
+int f32_launch_n13(const f32::Fast32Params &p, bool dit, int mode, int kind, int grid, void *stream);   // intfft_fast32_n13.cu
 
 }  // namespace intfft

@@ -5,6 +5,7 @@ import torch
 import intfftk_b200 as ib
 
 def time_plan(batch, steps=50, direction=0, **gk):
+    steps = int(os.environ.get("QT_STEPS", steps))
     g = ib.Generics(**gk)
     core = ib.Core(g, batch, direction)
     x, y = core.new_input(), core.new_output()
