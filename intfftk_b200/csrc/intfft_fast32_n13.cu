@@ -3,46 +3,38 @@
 // read from HBM once and written once (16 B instead of 32 B per sample at c5), and one of the two
 // load / store / address-generation sequences disappears.
 //
-// Shape: one CTA of 512 threads per SM owns an 8192-sample frame.  A thread keeps 16 samples in
-// registers; the 13 stages run as four register rounds
+// Shape: a CTA of 256 threads (two per SM, so one CTA's exchanges overlap the other's arithmetic) owns an
+// 8192-sample frame and walks its two 4096-sample halves one after the other.  A thread keeps 16 samples
+// in registers; per half, STAGE 0..11 run as three register rounds
 //     A: STAGE 0..3  (16 contiguous samples)        twiddles: kernel parameters (constant bank)
 //     B: STAGE 4..7  (stride 16)                    twiddles: 15 x 16 shared table (depend on tid & 15)
-//     C: STAGE 8..11 (stride 256)                   twiddles: 15 per-thread registers (depend on tid & 255)
-//     D: STAGE 12    (8 pairs i, i + 4096)          twiddles: 8 per-thread registers
-// DIT walks A -> D, DIF walks D -> A.  The three ownership changes (the delay-line commutations of
-// int_delay_line.vhd:52-104) go through a double-buffered, skewed shared-memory tile: one CTA barrier
-// each.  The next frame is prefetched with cp.async into thread-private staging slots while the current
-// one is being computed.  Arithmetic = intfft_fast32.cuh (fly32 / cmul32), i.e. int_dif2_fly.vhd:142-373,
-// int_dit2_fly.vhd:140-325, int_cmult_dsp48.vhd:182-190 / 307-317 and the dbl18 / dbl35 arrangements.
+//     C: STAGE 8..11 (stride 256)                   twiddles: 15 per-thread registers
+// and STAGE 12 pairs sample i of the lower half with i + 4096 of the upper half.  In round C's ownership
+// (tid + 256 m) both samples of every STAGE-12 pair belong to the SAME thread, so that stage needs no
+// exchange: one half's 16 samples wait in thread-private shared-memory slots while the other half is
+// computed.  DIT walks A, B, C per half and then STAGE 12; DIF starts with STAGE 12 and walks C, B, A.
+// Ownership changes (the delay-line commutations of int_delay_line.vhd:52-104): A <-> B stays inside a
+// half-warp (__syncwarp), B <-> C goes through a skewed shared tile under CTA barriers.
+// Arithmetic = intfft_fast32.cuh (fly32 / cmul32): int_dif2_fly.vhd:142-373, int_dit2_fly.vhd:140-325,
+// int_cmult_dsp48.vhd:182-190 / 307-317 and the dbl18 / dbl35 arrangements.
 #include "intfft_fast32.cuh"
 
 namespace intfft {
 
 namespace f32 {
 
-constexpr unsigned kTile13 = 9216;                         // >= phys8(8191) + 1
-constexpr unsigned kStage13 = 16 * 512 * 8;                // 16 slots x 512 threads x 8 bytes
-constexpr unsigned kSmem13 = kHead32 + 2 * kTile13 * 8 + kStage13;
-
-__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-
-// register m of round D: pair index j = m >> 1 (sample t + 512 j), upper / lower half = m & 1
-__host__ __device__ constexpr unsigned offD(int m) { return ((unsigned)(m >> 1) << 9) | ((unsigned)(m & 1) << 12); }
+constexpr unsigned kSmem13 = kHead32 + 2 * kTile8 * 8 + 16 * 256 * 8;   // table + tiles P, Q + private slots
 
 template <bool DIT, int MODE, int KIND>
-__global__ void __launch_bounds__(512, 1) fast32_n13_kernel(const __grid_constant__ Fast32Params p)
+__global__ void __launch_bounds__(256, 2) fast32_n13_kernel(const __grid_constant__ Fast32Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);                       // [15][16]
-    int2(*work)[kTile13] = reinterpret_cast<int2(*)[kTile13]>(smem_raw + kHead32);
-    unsigned char *stage = smem_raw + kHead32 + 2 * kTile13 * 8;
+    int2 *P = reinterpret_cast<int2 *>(smem_raw + kHead32);                       // A <-> B (warp-local)
+    int2 *Q = P + kTile8;                                                         // B <-> C
+    int2 *S = Q + kTile8;                                                         // [16][256] private slots
 
     const unsigned tid = threadIdx.x;
-    const int esz = 2 * p.in_sb;                                                  // bytes per complex sample read
 
     // ---- batch-invariant twiddles ----
     if (tid < 240) {                                   // round B: table[w][tid & 15], w = (1 << q) - 1 + j, STAGE 4 + q
@@ -51,149 +43,136 @@ __global__ void __launch_bounds__(512, 1) fast32_n13_kernel(const __grid_constan
         const int j = w - ((1 << q) - 1);
         midtw[w * 16 + lo4] = __ldg(p.tw + (1u << (4 + q)) + lo4 + ((unsigned)j << 4));
     }
-    int uwr[15], uwi[15];                              // round C: index (tid & 255) + 256 j at STAGE 8 + q
+    int uwr[15], uwi[15];                              // round C: index tid + 256 j at STAGE 8 + q
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int j = 0; j < (1 << q); ++j) {
-            const int2 w = __ldg(p.tw + (1u << (8 + q)) + (tid & 255u) + ((unsigned)j << 8));
+            const int2 w = __ldg(p.tw + (1u << (8 + q)) + tid + ((unsigned)j << 8));
             uwr[(1 << q) - 1 + j] = w.x;
             uwi[(1 << q) - 1 + j] = w.y;
         }
-    int dwr[8], dwi[8];                                // round D: index tid + 512 j at STAGE 12
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int2 w = __ldg(p.tw + (1u << 12) + tid + ((unsigned)j << 9));
-        dwr[j] = w.x;
-        dwi[j] = w.y;
-    }
     int lwr[15], lwi[15];
 #pragma unroll
     for (int i = 0; i < 15; ++i) { lwr[i] = p.lw_r[i]; lwi[i] = p.lw_i[i]; }
-
-    // ---- ownership (8-byte slots of the skewed tile) ----
-    const unsigned pA = phys8(16u * tid);
-    const unsigned pB = phys8((tid & 15u) | ((tid >> 4) << 8));
-    const unsigned pC = phys8((tid & 255u) | ((tid >> 8) << 12));
-    const unsigned pD = phys8(tid);
-
-    // ---- prefetch of a frame's first-round samples into this thread's staging slots ----
-    auto prefetch = [&](long long t) {
-        const char *src = reinterpret_cast<const char *>(p.in) + (t << 13) * esz;
-        if (DIT) {                                     // 16 contiguous samples = esz pieces of 16 bytes
-            src += (size_t)(16u * tid) * esz;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < esz) cp_async_16(stage + (j * 512 + tid) * 16, src + 16 * j);
-        } else {
-#pragma unroll
-            for (int m = 0; m < 16; ++m)
-                cp_async_elem(stage + (m * 512 + tid) * esz, src + (size_t)(tid + offD(m)) * esz, esz);
-        }
-        cp_async_commit();
-    };
-    if ((long long)blockIdx.x < p.n_tiles) prefetch(blockIdx.x);
+    const int2 *twD = p.tw + (1u << 12) + tid;         // STAGE 12: index tid + 256 m (read through L1 / L2 per frame)
     __syncthreads();
 
+    const unsigned pA = phys8(16u * tid);
+    const unsigned pB = phys8((tid & 15u) | ((tid >> 4) << 8));
+    const unsigned pC = phys8(tid);
     const Stg stD = stage_of<DIT, MODE, KIND>(p, 12);
 
-    int ex = 0;                                        // exchanges done so far: selects the buffer
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const long long g0 = tile << 13;
         V re[16], im[16];
 
-        // ---- first round's samples: drain the staging slots, refill them with the next frame ----
-        cp_async_wait_all();
-        if (DIT) {
-            if (p.in_sb == 4) {
+        if (!DIT) {
+            // ---- STAGE 12 first: lower-half results stay in registers, upper-half results wait in S ----
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int4 v = reinterpret_cast<const int4 *>(stage)[j * 512 + tid];
-                    re[2 * j] = mk(sx(v.x, p.dw)); im[2 * j] = mk(sx(v.y, p.dw));
-                    re[2 * j + 1] = mk(sx(v.z, p.dw)); im[2 * j + 1] = mk(sx(v.w, p.dw));
-                }
-            } else {
+            for (int m = 0; m < 16; ++m) {
+                int ar, ai, br, bi;
+                ld_sample(p.in, g0 + tid + 256u * m, p.in_sb, ar, ai);
+                ld_sample(p.in, g0 + 4096 + tid + 256u * m, p.in_sb, br, bi);
+                const int2 w = __ldg(twD + 256 * m);
+                V xr = mk(sx(ar, p.dw)), xi = mk(sx(ai, p.dw)), yr = mk(sx(br, p.dw)), yi = mk(sx(bi, p.dw));
+                fly32<DIT, MODE, KIND>(stD, false, p.cm, xr, xi, yr, yi, w.x, w.y);
+                re[m] = xr;
+                im[m] = xi;
+                S[m * 256 + tid] = make_int2(yr.f, yi.f);
+            }
+        }
+
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {                   // a real loop: keeps the body inside the 32 KB L1.5 I-cache
+            const long long gh = g0 + 4096 * h;
+            if (DIT) {
+                // ---- 16 contiguous samples straight from HBM ----
+                if (p.in_sb == 4) {
+                    const int4 *src = reinterpret_cast<const int4 *>(p.in) + ((gh + 16u * tid) >> 1);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint4 v = reinterpret_cast<const uint4 *>(stage)[j * 512 + tid];
-                    const unsigned x[4] = {v.x, v.y, v.z, v.w};
+                    for (int j = 0; j < 8; ++j) {
+                        const int4 v = __ldg(src + j);
+                        re[2 * j] = mk(sx(v.x, p.dw)); im[2 * j] = mk(sx(v.y, p.dw));
+                        re[2 * j + 1] = mk(sx(v.z, p.dw)); im[2 * j + 1] = mk(sx(v.w, p.dw));
+                    }
+                } else {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(p.in) + ((gh + 16u * tid) >> 2);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        re[4 * j + e] = mk(sx((int)x[e], p.dw));
-                        im[4 * j + e] = mk(sx((int)x[e] >> 16, p.dw));
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 v = __ldg(src + j);
+                        const unsigned x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            re[4 * j + e] = mk(sx((int)x[e], p.dw));
+                            im[4 * j + e] = mk(sx((int)x[e] >> 16, p.dw));
+                        }
                     }
                 }
-            }
-        } else {
+                round32<4, DIT, MODE, KIND>(re, im, p, 0, TwRegs32{lwr, lwi}, true, false);
+                __syncwarp();
 #pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                int a, b;
-                if (p.in_sb == 4) {
-                    const int2 v = reinterpret_cast<const int2 *>(stage)[m * 512 + tid];
-                    a = v.x; b = v.y;
+                for (int m = 0; m < 16; ++m) P[pA + m] = make_int2(re[m].f, im[m].f);
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < 16; ++m) { const int2 v = P[pB + 18u * m]; re[m] = mk(v.x); im[m] = mk(v.y); }
+                round32<4, DIT, MODE, KIND>(re, im, p, 4, TwSmem32{midtw + (tid & 15u), 16}, false, false);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) Q[pB + 18u * m] = make_int2(re[m].f, im[m].f);
+                __syncthreads();
+#pragma unroll
+                for (int m = 0; m < 16; ++m) { const int2 v = Q[pC + 288u * m]; re[m] = mk(v.x); im[m] = mk(v.y); }
+                __syncthreads();                           // Q may be rewritten once every thread has read it
+                round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
+                if (h == 0) {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) S[m * 256 + tid] = make_int2(re[m].f, im[m].f);
                 } else {
-                    const unsigned x = reinterpret_cast<const unsigned *>(stage)[m * 512 + tid];
-                    a = (int)x; b = (int)x >> 16;
+                    // ---- STAGE 12 between the parked lower half and the registers; coalesced stores ----
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        const int2 a = S[m * 256 + tid];
+                        const int2 w = __ldg(twD + 256 * m);
+                        V xr = mk(a.x), xi = mk(a.y);
+                        fly32<DIT, MODE, KIND>(stD, false, p.cm, xr, xi, re[m], im[m], w.x, w.y);
+                        st_sample(p.out, g0 + tid + 256u * m, p.out_sb, xr.f, xi.f);
+                        st_sample(p.out, g0 + 4096 + tid + 256u * m, p.out_sb, re[m].f, im[m].f);
+                    }
                 }
-                re[m] = mk(sx(a, p.dw));
-                im[m] = mk(sx(b, p.dw));
+            } else {
+                if (h == 1) {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) { const int2 v = S[m * 256 + tid]; re[m] = mk(v.x); im[m] = mk(v.y); }
+                }
+                round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) Q[pC + 288u * m] = make_int2(re[m].f, im[m].f);
+                __syncthreads();
+#pragma unroll
+                for (int m = 0; m < 16; ++m) { const int2 v = Q[pB + 18u * m]; re[m] = mk(v.x); im[m] = mk(v.y); }
+                __syncthreads();
+                round32<4, DIT, MODE, KIND>(re, im, p, 4, TwSmem32{midtw + (tid & 15u), 16}, false, false);
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < 16; ++m) P[pB + 18u * m] = make_int2(re[m].f, im[m].f);
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < 16; ++m) { const int2 v = P[pA + m]; re[m] = mk(v.x); im[m] = mk(v.y); }
+                round32<4, DIT, MODE, KIND>(re, im, p, 0, TwRegs32{lwr, lwi}, true, false);
+                if (p.out_sb == 4) {
+                    int4 *dst = reinterpret_cast<int4 *>(p.out) + ((gh + 16u * tid) >> 1);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_int4(re[2 * j].f, im[2 * j].f, re[2 * j + 1].f, im[2 * j + 1].f);
+                } else {
+                    uint4 *dst = reinterpret_cast<uint4 *>(p.out) + ((gh + 16u * tid) >> 2);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        dst[j] = make_uint4(__byte_perm((unsigned)re[4 * j].f, (unsigned)im[4 * j].f, 0x5410),
+                                            __byte_perm((unsigned)re[4 * j + 1].f, (unsigned)im[4 * j + 1].f, 0x5410),
+                                            __byte_perm((unsigned)re[4 * j + 2].f, (unsigned)im[4 * j + 2].f, 0x5410),
+                                            __byte_perm((unsigned)re[4 * j + 3].f, (unsigned)im[4 * j + 3].f, 0x5410));
+                }
             }
-        }
-        {
-            const long long nt = tile + gridDim.x;
-            if (nt < p.n_tiles) prefetch(nt);
-        }
-
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const int r = DIT ? rr : 3 - rr;               // 0 = A, 1 = B, 2 = C, 3 = D
-            if (r == 0) round32<4, DIT, MODE, KIND>(re, im, p, 0, TwRegs32{lwr, lwi}, true, false);
-            else if (r == 1) round32<4, DIT, MODE, KIND>(re, im, p, 4, TwSmem32{midtw + (tid & 15u), 16}, false, false);
-            else if (r == 2) round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
-            else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    fly32<DIT, MODE, KIND>(stD, false, p.cm, re[2 * j], im[2 * j], re[2 * j + 1], im[2 * j + 1], dwr[j], dwi[j]);
-            }
-            if (rr == 3) break;
-            // ---- ownership change r -> next round ----
-            const int rn = DIT ? r + 1 : r - 1;
-            int2 *sm = work[ex & 1];
-            ++ex;
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const unsigned a = r == 0 ? pA + m : (r == 1 ? pB + 18u * m : (r == 2 ? pC + 288u * m : pD + phys8(offD(m))));
-                sm[a] = make_int2(re[m].f, im[m].f);
-            }
-            // rounds A, B, C never leave a 4096-sample half, and thread half == sample half in all three
-            // layouts: those two changes only need the 256 threads of the half (named barrier 1 / 2)
-            if (r == 3 || rn == 3) __syncthreads();
-            else asm volatile("bar.sync %0, 256;" ::"r"(1 + (int)(tid >> 8)) : "memory");
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const unsigned a = rn == 0 ? pA + m : (rn == 1 ? pB + 18u * m : (rn == 2 ? pC + 288u * m : pD + phys8(offD(m))));
-                const int2 v = sm[a];
-                re[m] = mk(v.x);
-                im[m] = mk(v.y);
-            }
-        }
-
-        // ---- results ----
-        if (DIT) {                                         // round D ownership: coalesced element stores
-#pragma unroll
-            for (int m = 0; m < 16; ++m) st_sample(p.out, g0 + tid + offD(m), p.out_sb, re[m].f, im[m].f);
-        } else if (p.out_sb == 4) {                        // round A ownership: 16 contiguous samples per thread
-            int4 *dst = reinterpret_cast<int4 *>(p.out) + ((g0 + 16u * tid) >> 1);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_int4(re[2 * j].f, im[2 * j].f, re[2 * j + 1].f, im[2 * j + 1].f);
-        } else {
-            uint4 *dst = reinterpret_cast<uint4 *>(p.out) + ((g0 + 16u * tid) >> 2);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                dst[j] = make_uint4(__byte_perm((unsigned)re[4 * j].f, (unsigned)im[4 * j].f, 0x5410),
-                                    __byte_perm((unsigned)re[4 * j + 1].f, (unsigned)im[4 * j + 1].f, 0x5410),
-                                    __byte_perm((unsigned)re[4 * j + 2].f, (unsigned)im[4 * j + 2].f, 0x5410),
-                                    __byte_perm((unsigned)re[4 * j + 3].f, (unsigned)im[4 * j + 3].f, 0x5410));
         }
     }
 }
@@ -202,7 +181,7 @@ template <typename K> cudaError_t launch_n13(K k, const Fast32Params &p, int gri
 {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem13);
     if (e != cudaSuccess) return e;
-    k<<<grid, 512, kSmem13, st>>>(p);
+    k<<<grid, 256, kSmem13, st>>>(p);
     return cudaGetLastError();
 }
 
