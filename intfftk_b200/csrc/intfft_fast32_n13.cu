@@ -23,6 +23,12 @@ namespace intfft {
 
 namespace f32 {
 
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 constexpr unsigned kSmem13 = kHead32 + 2 * kTile8 * 8 + 16 * 256 * 8;   // table + tiles P, Q + private slots
 
 template <bool DIT, int MODE, int KIND>
@@ -63,6 +69,24 @@ __global__ void __launch_bounds__(256, 2) fast32_n13_kernel(const __grid_constan
     const unsigned pC = phys8(tid);
     const Stg stD = stage_of<DIT, MODE, KIND>(p, 12);
 
+    // DIT: cp.async prefetch of one half's first-round input (16 contiguous samples per thread) as 16-byte
+    // pieces into slots dst[piece * pitch]; packed 16-bit input uses pieces 4..7 (see the swap above)
+    int4 *S16 = reinterpret_cast<int4 *>(S);
+    int4 *P16 = reinterpret_cast<int4 *>(P + 576u * (tid >> 5));                  // this warp's 512-sample region of P
+    const unsigned lane = tid & 31u;
+    auto prefetch = [&](int4 *dst, int pitch, long long first_sample) {
+        const char *src = reinterpret_cast<const char *>(p.in) + (first_sample + 16u * tid) * (2 * p.in_sb);
+        if (p.in_sb == 4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cp_async_16(dst + j * pitch, src + 16 * j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cp_async_16(dst + (4 + j) * pitch, src + 16 * j);
+        }
+        cp_async_commit();
+    };
+    if (DIT && (long long)blockIdx.x < p.n_tiles) prefetch(P16 + lane, 32, (long long)blockIdx.x << 13);
+
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const long long g0 = tile << 13;
         V re[16], im[16];
@@ -83,32 +107,46 @@ __global__ void __launch_bounds__(256, 2) fast32_n13_kernel(const __grid_constan
             }
         }
 
+        if (DIT) {
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {                   // a real loop: keeps the body inside the 32 KB L1.5 I-cache
-            const long long gh = g0 + 4096 * h;
-            if (DIT) {
-                // ---- 16 contiguous samples straight from HBM ----
+            for (int h = 0; h < 2; ++h) {                 // a real loop: keeps the body inside the 32 KB L1.5 I-cache
+                // ---- this half's 16 contiguous samples were prefetched (cp.async) into private 16-byte slots:
+                // ---- lower half -> this warp's region of P, upper half -> S, where they now trade places with
+                // ---- the lower half's round-C results (which wait there for STAGE 12)
+                cp_async_wait_all();
                 if (p.in_sb == 4) {
-                    const int4 *src = reinterpret_cast<const int4 *>(p.in) + ((gh + 16u * tid) >> 1);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int4 v = __ldg(src + j);
+                        int4 v;
+                        if (h == 0) {
+                            v = P16[j * 32 + lane];
+                        } else {
+                            v = S16[j * 256 + tid];
+                            S16[j * 256 + tid] = make_int4(re[2 * j].f, im[2 * j].f, re[2 * j + 1].f, im[2 * j + 1].f);
+                        }
                         re[2 * j] = mk(sx(v.x, p.dw)); im[2 * j] = mk(sx(v.y, p.dw));
                         re[2 * j + 1] = mk(sx(v.z, p.dw)); im[2 * j + 1] = mk(sx(v.w, p.dw));
                     }
-                } else {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(p.in) + ((gh + 16u * tid) >> 2);
+                } else {                                   // packed 16-bit input: 4 pieces, parked in slots 4..7
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint4 v = __ldg(src + j);
-                        const unsigned x[4] = {v.x, v.y, v.z, v.w};
+                        int4 v;
+                        if (h == 0) {
+                            v = P16[(4 + j) * 32 + lane];
+                        } else {
+                            v = S16[(4 + j) * 256 + tid];
+                            S16[(2 * j) * 256 + tid] = make_int4(re[4 * j].f, im[4 * j].f, re[4 * j + 1].f, im[4 * j + 1].f);
+                            S16[(2 * j + 1) * 256 + tid] = make_int4(re[4 * j + 2].f, im[4 * j + 2].f, re[4 * j + 3].f, im[4 * j + 3].f);
+                        }
+                        const int x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            re[4 * j + e] = mk(sx((int)x[e], p.dw));
-                            im[4 * j + e] = mk(sx((int)x[e] >> 16, p.dw));
+                            re[4 * j + e] = mk(sx(x[e], p.dw));
+                            im[4 * j + e] = mk(sx(x[e] >> 16, p.dw));
                         }
                     }
                 }
+                if (h == 0) prefetch(S16 + tid, 256, g0 + 4096);
                 round32<4, DIT, MODE, KIND>(re, im, p, 0, TwRegs32{lwr, lwi}, true, false);
                 __syncwarp();
 #pragma unroll
@@ -116,6 +154,10 @@ __global__ void __launch_bounds__(256, 2) fast32_n13_kernel(const __grid_constan
                 __syncwarp();
 #pragma unroll
                 for (int m = 0; m < 16; ++m) { const int2 v = P[pB + 18u * m]; re[m] = mk(v.x); im[m] = mk(v.y); }
+                if (h == 1) {                              // P is idle until the next frame's A -> B change
+                    __syncwarp();
+                    if (tile + gridDim.x < p.n_tiles) prefetch(P16 + lane, 32, (tile + gridDim.x) << 13);
+                }
                 round32<4, DIT, MODE, KIND>(re, im, p, 4, TwSmem32{midtw + (tid & 15u), 16}, false, false);
 #pragma unroll
                 for (int m = 0; m < 16; ++m) Q[pB + 18u * m] = make_int2(re[m].f, im[m].f);
@@ -124,22 +166,28 @@ __global__ void __launch_bounds__(256, 2) fast32_n13_kernel(const __grid_constan
                 for (int m = 0; m < 16; ++m) { const int2 v = Q[pC + 288u * m]; re[m] = mk(v.x); im[m] = mk(v.y); }
                 __syncthreads();                           // Q may be rewritten once every thread has read it
                 round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
-                if (h == 0) {
+            }
+            // ---- STAGE 12 between the parked lower half and the registers; coalesced stores ----
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) S[m * 256 + tid] = make_int2(re[m].f, im[m].f);
-                } else {
-                    // ---- STAGE 12 between the parked lower half and the registers; coalesced stores ----
+            for (int j = 0; j < 8; ++j) {
+                const int4 a = S16[j * 256 + tid];
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) {
-                        const int2 a = S[m * 256 + tid];
-                        const int2 w = __ldg(twD + 256 * m);
-                        V xr = mk(a.x), xi = mk(a.y);
-                        fly32<DIT, MODE, KIND>(stD, false, p.cm, xr, xi, re[m], im[m], w.x, w.y);
-                        st_sample(p.out, g0 + tid + 256u * m, p.out_sb, xr.f, xi.f);
-                        st_sample(p.out, g0 + 4096 + tid + 256u * m, p.out_sb, re[m].f, im[m].f);
-                    }
+                for (int e = 0; e < 2; ++e) {
+                    const int m = 2 * j + e;
+                    const int2 w = __ldg(twD + 256 * m);
+                    V xr = mk(e ? a.z : a.x), xi = mk(e ? a.w : a.y);
+                    fly32<DIT, MODE, KIND>(stD, false, p.cm, xr, xi, re[m], im[m], w.x, w.y);
+                    st_sample(p.out, g0 + tid + 256u * m, p.out_sb, xr.f, xi.f);
+                    st_sample(p.out, g0 + 4096 + tid + 256u * m, p.out_sb, re[m].f, im[m].f);
                 }
-            } else {
+            }
+            continue;
+        }
+
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const long long gh = g0 + 4096 * h;
+            {
                 if (h == 1) {
 #pragma unroll
                     for (int m = 0; m < 16; ++m) { const int2 v = S[m * 256 + tid]; re[m] = mk(v.x); im[m] = mk(v.y); }
