@@ -58,6 +58,7 @@ enum { KIND_SINGLE = 0, KIND_MIXED = 1 };
 
 struct Stg {
     int s, ow, dtwc, kind;
+    int k, sp;               // KIND_MIXED: pre-shift of each product and post-shift of their sum (grid-uniform)
 };
 template <bool DIT, int MODE, int KIND>
 __device__ __forceinline__ Stg stage_of(const Fast32Params &p, int s)
@@ -70,13 +71,15 @@ __device__ __forceinline__ Stg stage_of(const Fast32Params &p, int s)
     st.ow = dtw + FORMAT;
     st.dtwc = DIT ? dtw : st.ow;
     st.kind = (KIND == KIND_SINGLE) ? 0 : (st.dtwc < p.cm.lim_single ? 0 : 1);
+    // the single arrangement is the double one with no pre-shift: (P2 +- P1) >> sh == ((P2 >> 0) +- (P1 >> 0)) >> sh,
+    // so a pass that mixes both runs ONE branch-free code path with per-stage shift amounts
+    st.k = st.kind ? p.cm.k_pre : 0;
+    st.sp = st.kind ? p.cm.sh_post : p.cm.sh_single;
     return st;
 }
 
 __device__ __forceinline__ int negq32(int v) { return (v >> 31) - v; }
 
-// double-DSP arrangement (rare: only stages whose operand is >= 28 / 26 / 19 bits wide); kept out of
-// line so the common single-DSP path stays branch-free and small
 // bits [sh+w-1 : sh] of a 64-bit value, sign-extended: funnel-left by 64-sh-w (high word), then an
 // arithmetic right shift by 32-w  (bfe.s32 with a register length costs three instructions instead)
 __device__ __forceinline__ int field(long long t, int sh, int w)
@@ -87,26 +90,32 @@ __device__ __forceinline__ int field(long long t, int sh, int w)
 // low w bits of a 32-bit value, sign-extended
 __device__ __forceinline__ int sx(int v, int w) { return (int)((unsigned)v << (32 - w)) >> (32 - w); }
 
-template <int MODE>
-__device__ __noinline__ void cmul32_dbl(int dr, int di, int wr, int wi, int k_pre, int sh_post, int dtwc, int (&o)[4])
+// exact signed 32 x 32 -> 64 (asm: next to word-wise shifts the front end otherwise emits IMAD.WIDE.U32 + fix-ups)
+__device__ __forceinline__ long long mulw(int a, int b)
 {
-    const long long tr = (((long long)dr * wr) >> k_pre) - (((long long)di * wi) >> k_pre);
-    const long long ti = (((long long)dr * wi) >> k_pre) + (((long long)di * wr) >> k_pre);
-    o[0] = field(tr, sh_post, dtwc);
-    o[1] = field(ti, sh_post, dtwc);
-    o[2] = MODE == MODE_TRUNC ? field(tr, sh_post + 1, dtwc - 1) : 0;
-    o[3] = MODE == MODE_TRUNC ? field(ti, sh_post + 1, dtwc - 1) : 0;
+    long long r;
+    asm("mul.wide.s32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+// t >> k for 0 <= k < 32 (every pre-shift of the double arrangements is below 32)
+__device__ __forceinline__ long long sra64(long long t, int k)
+{
+    const unsigned lo = __funnelshift_r((unsigned)t, (unsigned)(t >> 32), k);
+    const int hi = (int)(t >> 32) >> k;
+    return (long long)(((unsigned long long)(unsigned)hi << 32) | lo);
 }
 
 template <int MODE, int KIND>
 __device__ __forceinline__ void cmul32(int dr, int di, int wr, int wi, const CmultConsts &cm, const Stg &st,
                                        V &o_re, V &o_im)
 {
-    if (KIND == KIND_MIXED && st.kind != 0) {
-        int o[4];
-        cmul32_dbl<MODE>(dr, di, wr, wi, cm.k_pre, cm.sh_post, st.dtwc, o);
-        o_re = V{o[0], o[2]};
-        o_im = V{o[1], o[3]};
+    if (KIND == KIND_MIXED) {                   // double (or single as its k = 0 case), int_cmult_dbl18/dbl35
+        const long long tr = sra64(mulw(dr, wr), st.k) - sra64(mulw(di, wi), st.k);
+        const long long ti = sra64(mulw(dr, wi), st.k) + sra64(mulw(di, wr), st.k);
+        o_re.f = field(tr, st.sp, st.dtwc);
+        o_im.f = field(ti, st.sp, st.dtwc);
+        o_re.h = MODE == MODE_TRUNC ? field(tr, st.sp + 1, st.dtwc - 1) : 0;
+        o_im.h = MODE == MODE_TRUNC ? field(ti, st.sp + 1, st.dtwc - 1) : 0;
         return;
     }
     const long long tr = (long long)dr * wr - (long long)di * wi;      // 2 x IMAD.WIDE

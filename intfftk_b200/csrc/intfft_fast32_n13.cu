@@ -181,9 +181,7 @@ __global__ void __launch_bounds__(256, 2) fast32_n13_kernel(const __grid_constan
                     st_sample(p.out, g0 + 4096 + tid + 256u * m, p.out_sb, re[m].f, im[m].f);
                 }
             }
-            continue;
-        }
-
+        } else {
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             const long long gh = g0 + 4096 * h;
@@ -221,6 +219,7 @@ __global__ void __launch_bounds__(256, 2) fast32_n13_kernel(const __grid_constan
                                             __byte_perm((unsigned)re[4 * j + 3].f, (unsigned)im[4 * j + 3].f, 0x5410));
                 }
             }
+        }
         }
     }
 }
