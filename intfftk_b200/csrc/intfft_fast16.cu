@@ -398,6 +398,27 @@ struct Strided16Params {
     int dw, sh_full, sh_half;
 };
 
+// Shared memory of the strided pass: [head | exchange tile | 2 x landing tile]; all three tiles use the
+// phys() skew, so a landing tile is read exactly like the exchange tile.
+constexpr unsigned kStridedSmem = kSmemHead + 3 * kTileWords * 4;
+
+__device__ __forceinline__ void cp_async_16(uint32_t *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// the 16 stores of a strided pass's last round: register m goes 2^SHIFT m rows below register 0; with the
+// row pitch a compile-time constant (PB = NFFT - G = 9..12) every offset is an instruction immediate
+template <int PB, int SHIFT>
+__device__ __forceinline__ void store_rows(char *ptr, const int (&re)[16], const int (&im)[16])
+{
+#pragma unroll
+    for (int m = 0; m < 16; ++m)
+        *reinterpret_cast<uint32_t *>(ptr + ((((size_t)m << SHIFT) << PB) << 2)) = pack(re[m], im[m]);
+}
+
 template <int G, bool DIT, bool DW16, int MODE>
 __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_constant__ Strided16Params p)
 {
@@ -405,14 +426,14 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
     constexpr int NR = G / 4;                       // rounds: local bits [8,12) and, for G = 8, [4,8)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);
-    uint32_t(*work)[kTileWords] = reinterpret_cast<uint32_t(*)[kTileWords]>(smem_raw + kSmemHead);
+    uint32_t *work = reinterpret_cast<uint32_t *>(smem_raw + kSmemHead);
+    uint32_t(*land)[kTileWords] = reinterpret_cast<uint32_t(*)[kTileWords]>(smem_raw + kSmemHead + kTileWords * 4);
 
     const unsigned tid = threadIdx.x;
     const int sh_full = p.sh_full, sh_half = p.sh_half;
     const int pb = p.n - G;                         // lowest global bit of this pass
     const unsigned cmask = (1u << C) - 1u;
     const int mid_bits = pb - C;
-    const long long row_stride = 1ll << pb;
 
     int it = 0;
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
@@ -421,6 +442,23 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
         const long long f1 = (f0 + p.frames_per_unit < p.batch) ? f0 + p.frames_per_unit : p.batch;
         // twiddle index of local position l (only its bits below the stage bit matter)
         auto kidx = [&](unsigned l) { return ((l >> C) << pb) | (mid << C) | (l & cmask); };
+
+        // One frame's 2^G x 2^C column block -> a landing tile, as 16-byte cp.async pieces (4 per thread;
+        // a piece never straddles a row because C >= 2).  The copy of frame f + 1 is in flight while
+        // frame f is computed; the CTA barrier at the top of a frame publishes the landed pieces and
+        // also orders the single exchange tile's reuse.
+        // Addresses inside a frame are 32-bit byte offsets from a CTA-uniform 64-bit base (a frame is at
+        // most 4 MB), so each access costs one integer add instead of a 64-bit multiply-add.
+        auto prefetch = [&](uint32_t *dst, long long f) {
+            const char *src = reinterpret_cast<const char *>(p.in + (f << p.n) + ((long long)mid << C));
+            const unsigned l0 = 4u * tid;
+            const unsigned b0 = ((l0 >> C) << (pb + 2)) + ((l0 & cmask) << 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)       // piece j: local index l0 + 1024 j, i.e. 2^(10-C) j rows further down
+                cp_async_16(dst + phys(4u * tid) + phys(1024u * j), src + (b0 + (((unsigned)j << (10 - C)) << (pb + 2))));
+            cp_async_commit();
+        };
+        if (f0 < f1) prefetch(land[it & 1], f0);
 
         // ---- twiddles of this column block ----
         int uwr[15], uwi[15];                       // top round: local bits 8..11
@@ -442,12 +480,14 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
                 const int sgl = pb + (4 + q - C);
                 midtw[w * 16 + lo4] = __ldg(p.twp + (1u << sgl) + (kidx((unsigned)lo4 | ((unsigned)j << 4)) & ((1u << sgl) - 1u)));
             }
-            __syncthreads();
         }
 
         for (long long f = f0; f < f1; ++f, ++it) {
-            uint32_t *sm = work[it & 1];
-            const long long gbase = (f << p.n) + ((long long)mid << C);
+            cp_async_wait_all();
+            __syncthreads();
+            const uint32_t *st = land[it & 1];
+            if (f + 1 < f1) prefetch(land[(it + 1) & 1], f + 1);
+            char *obase = reinterpret_cast<char *>(p.out + (f << p.n) + ((long long)mid << C));
             int re[16], im[16];
 #pragma unroll
             for (int rr = 0; rr < NR; ++rr) {
@@ -458,27 +498,31 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
                 const unsigned pbase = phys(base);
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
-                    const unsigned l = base | ((unsigned)m << lo);
-                    uint32_t x;
-                    if (first) x = __ldg(p.in + gbase + (long long)(l >> C) * row_stride + (l & cmask));
-                    else x = sm[pbase + phys((unsigned)m << lo)];
+                    const uint32_t x = (first ? st : work)[pbase + phys((unsigned)m << lo)];
                     unpack<DW16>(x, p.dw, re[m], im[m]);
                 }
                 constexpr bool RAW = !DIT && DW16;
                 if (lo == 8) round_regs<8, 4, DIT, DW16, MODE, RAW && (NR == 2)>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
                 else round_regs<4, 4, DIT, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, false, sh_full, sh_half);
+                if (last) {
+                    // register m sits 2^(lo-C) m rows below register 0 (lo >= C in every geometry)
+                    constexpr int SHIFT = (G == 8 && DIT) ? 4 : 0;
+                    char *ptr = obase + (((base >> C) << (pb + 2)) + ((base & cmask) << 2));
+                    switch (pb) {
+                    case 9: store_rows<9, SHIFT>(ptr, re, im); break;
+                    case 10: store_rows<10, SHIFT>(ptr, re, im); break;
+                    case 11: store_rows<11, SHIFT>(ptr, re, im); break;
+                    default: store_rows<12, SHIFT>(ptr, re, im); break;
+                    }
+                } else {
 #pragma unroll
-                for (int m = 0; m < 16; ++m) {
-                    const unsigned l = base | ((unsigned)m << lo);
-                    if (last) {
-                        p.out[gbase + (long long)(l >> C) * row_stride + (l & cmask)] = pack(re[m], im[m]);
-                    } else {
+                    for (int m = 0; m < 16; ++m) {
                         const uint32_t x = (RAW && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632)
                                                             : pack(re[m], im[m]);
-                        sm[pbase + phys((unsigned)m << lo)] = x;
+                        work[pbase + phys((unsigned)m << lo)] = x;
                     }
+                    __syncthreads();
                 }
-                if (!last) __syncthreads();
             }
         }
     }
@@ -487,7 +531,7 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
 template <int G, bool DIT, bool DW16>
 cudaError_t launch_strided_k(const Strided16Params &p, int mode, int grid, cudaStream_t st)
 {
-    const int smem = kSmemHead + 2 * kTileWords * 4;
+    const int smem = (int)kStridedSmem;
     auto k = mode == MODE_ROUND ? fast16_strided_kernel<G, DIT, DW16, MODE_ROUND> : fast16_strided_kernel<G, DIT, DW16, MODE_TRUNC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;

@@ -154,7 +154,9 @@ template <int MODE> __device__ __forceinline__ void addsub32(const V &a, const V
     y = mk(yf);
 }
 
-template <bool DIT, int MODE, int KIND>
+// MUL: the caller knows st.s >= 2 (every stage of a strided top pass), so the multiplier-free STAGE 0 / 1
+// forms are not even compiled in and the butterflies of a round form one basic block
+template <bool DIT, int MODE, int KIND, bool MUL = false>
 __device__ __forceinline__ void fly32(const Stg &st, bool odd, const CmultConsts &cm, V &ar, V &ai, V &br, V &bi,
                                       int wr, int wi)
 {
@@ -164,10 +166,10 @@ __device__ __forceinline__ void fly32(const Stg &st, bool odd, const CmultConsts
         addsub32<MODE>(ai, bi, st.ow, xi, si);
         ar = xr;
         ai = xi;
-        if (st.s == 0) {
+        if (!MUL && st.s == 0) {
             br = sr;
             bi = si;
-        } else if (st.s == 1) {
+        } else if (!MUL && st.s == 1) {
             br = odd ? si : sr;
             bi = odd ? mk(negq32(sr.f)) : si;
         } else {
@@ -175,10 +177,10 @@ __device__ __forceinline__ void fly32(const Stg &st, bool odd, const CmultConsts
         }
     } else {
         V wr_, wi_;                                   // BW
-        if (st.s == 0) {
+        if (!MUL && st.s == 0) {
             wr_ = br;
             wi_ = bi;
-        } else if (st.s == 1) {
+        } else if (!MUL && st.s == 1) {
             wr_ = odd ? mk(negq32(bi.f)) : br;
             wi_ = odd ? br : bi;
         } else {                                      // DI_RE <= IB_IM, DI_IM <= IB_RE; DO_RE => bw_im, DO_IM => bw_re
@@ -238,7 +240,7 @@ struct TwSmem32 {
 };
 
 // R stages on register bits 0..R-1 (global stage numbers S0 .. S0+R-1) of the 16 resident samples
-template <int R, bool DIT, int MODE, int KIND, typename TW>
+template <int R, bool DIT, int MODE, int KIND, typename TW, bool MUL = false>
 __device__ __forceinline__ void round32(V (&re)[16], V (&im)[16], const Fast32Params &p, int s0, const TW &tw,
                                         bool lo_is_zero, bool tid_odd)
 {
@@ -251,9 +253,9 @@ __device__ __forceinline__ void round32(V (&re)[16], V (&im)[16], const Fast32Pa
             if (m & (1 << q)) continue;
             const int w = (1 << q) - 1 + (m & ((1 << q) - 1));
             int wr = 0, wi = 0;
-            if (st.s >= 2) tw(w, wr, wi);
+            if (MUL || st.s >= 2) tw(w, wr, wi);
             const bool odd = lo_is_zero ? ((m & 1) != 0) : tid_odd;
-            fly32<DIT, MODE, KIND>(st, odd, p.cm, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi);
+            fly32<DIT, MODE, KIND, MUL>(st, odd, p.cm, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi);
         }
     }
 }
@@ -416,6 +418,23 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
     }
 }
 
+// the 16 stores of a strided pass's last round: register m goes 2^SHIFT m rows below register 0; with the
+// row pitch a compile-time constant (PB = NFFT - G) every offset is an instruction immediate, and the
+// container size is tested once, not per sample
+template <int PB, int SHIFT>
+__device__ __forceinline__ void store_rows32(char *ptr, int sb, const V (&re)[16], const V (&im)[16])
+{
+    if (sb == 2) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m)
+            *reinterpret_cast<unsigned *>(ptr + ((((size_t)m << SHIFT) << PB) << 2)) = __byte_perm((unsigned)re[m].f, (unsigned)im[m].f, 0x5410);
+    } else {
+#pragma unroll
+        for (int m = 0; m < 16; ++m)
+            *reinterpret_cast<int2 *>(ptr + ((((size_t)m << SHIFT) << PB) << 3)) = make_int2(re[m].f, im[m].f);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // strided pass: the top G = 4 or 8 stage bits of an NFFT = 13..20 transform (see intfft_fast16.cu)
 template <int G, bool DIT, int MODE, int KIND>
@@ -505,15 +524,25 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_kernel(const __grid_con
                     im[m] = mk(b);
                 }
                 if (first && f + 1 < f1) prefetch(f + 1);
-                if (lo == 8) round32<4, DIT, MODE, KIND>(re, im, p, pb + 8 - C, TwRegs32{uwr, uwi}, false, false);
-                else round32<4, DIT, MODE, KIND>(re, im, p, pb + 4 - C, TwSmem32{midtw + (tid & 15u), 16}, false, false);
+                // every stage of this pass is a multiplying one: STAGE >= NFFT - 8 >= 5
+                if (lo == 8) round32<4, DIT, MODE, KIND, TwRegs32, true>(re, im, p, pb + 8 - C, TwRegs32{uwr, uwi}, false, false);
+                else round32<4, DIT, MODE, KIND, TwSmem32, true>(re, im, p, pb + 4 - C, TwSmem32{midtw + (tid & 15u), 16}, false, false);
+                if (last) {
+                    constexpr int SHIFT = (G == 8 && DIT) ? 4 : 0;          // lo - C of the last round
+                    char *ptr = reinterpret_cast<char *>(p.out) +
+                                (gbase + (long long)(base >> C) * row_stride + (base & cmask)) * (2 * p.out_sb);
+                    switch (pb) {
+                    case 8: store_rows32<8, SHIFT>(ptr, p.out_sb, re, im); break;
+                    case 9: store_rows32<9, SHIFT>(ptr, p.out_sb, re, im); break;
+                    case 10: store_rows32<10, SHIFT>(ptr, p.out_sb, re, im); break;
+                    case 11: store_rows32<11, SHIFT>(ptr, p.out_sb, re, im); break;
+                    default: store_rows32<12, SHIFT>(ptr, p.out_sb, re, im); break;
+                    }
+                } else {
 #pragma unroll
-                for (int m = 0; m < 16; ++m) {
-                    const unsigned l = base | ((unsigned)m << lo);
-                    if (last) st_sample(p.out, gbase + (long long)(l >> C) * row_stride + (l & cmask), p.out_sb, re[m].f, im[m].f);
-                    else sm[pbase + phys8((unsigned)m << lo)] = make_int2(re[m].f, im[m].f);
+                    for (int m = 0; m < 16; ++m) sm[pbase + phys8((unsigned)m << lo)] = make_int2(re[m].f, im[m].f);
+                    __syncthreads();
                 }
-                if (!last) __syncthreads();
             }
         }
     }

@@ -29,16 +29,20 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
-constexpr unsigned kSmem13 = kHead32 + 2 * kTile8 * 8 + 16 * 256 * 8;   // table + tiles P, Q + private slots
+constexpr int kCtas13 = 3;
+constexpr unsigned kSmem13 = kHead32 + kTile8 * 8 + 16 * 256 * 8;   // table + exchange tile + private slots (70 KB: 3 CTAs / SM)
 
 template <bool DIT, int MODE, int KIND>
-__global__ void __launch_bounds__(256, 2) fast32_n13_kernel(const __grid_constant__ Fast32Params p)
+__global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_constant__ Fast32Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);                       // [15][16]
+    // ONE exchange tile serves both ownership changes of a half: A <-> B stays inside a warp's 512-sample
+    // region, and the B-side of B <-> C is in place (a thread writes / reads exactly the slots it read /
+    // will write as the A <-> B partner), so the only cross-warp hazards are the two guarded by CTA barriers
     int2 *P = reinterpret_cast<int2 *>(smem_raw + kHead32);                       // A <-> B (warp-local)
-    int2 *Q = P + kTile8;                                                         // B <-> C
-    int2 *S = Q + kTile8;                                                         // [16][256] private slots
+    int2 *Q = P;                                                                  // B <-> C
+    int2 *S = P + kTile8;                                                         // [16][256] private slots
 
     const unsigned tid = threadIdx.x;
 
@@ -154,17 +158,15 @@ __global__ void __launch_bounds__(256, 2) fast32_n13_kernel(const __grid_constan
                 __syncwarp();
 #pragma unroll
                 for (int m = 0; m < 16; ++m) { const int2 v = P[pB + 18u * m]; re[m] = mk(v.x); im[m] = mk(v.y); }
-                if (h == 1) {                              // P is idle until the next frame's A -> B change
-                    __syncwarp();
-                    if (tile + gridDim.x < p.n_tiles) prefetch(P16 + lane, 32, (tile + gridDim.x) << 13);
-                }
                 round32<4, DIT, MODE, KIND>(re, im, p, 4, TwSmem32{midtw + (tid & 15u), 16}, false, false);
 #pragma unroll
                 for (int m = 0; m < 16; ++m) Q[pB + 18u * m] = make_int2(re[m].f, im[m].f);
                 __syncthreads();
 #pragma unroll
                 for (int m = 0; m < 16; ++m) { const int2 v = Q[pC + 288u * m]; re[m] = mk(v.x); im[m] = mk(v.y); }
-                __syncthreads();                           // Q may be rewritten once every thread has read it
+                __syncthreads();                           // the tile may be rewritten once every thread has read it
+                // the tile is idle until the next frame's A -> B change: land that frame's lower half in it
+                if (h == 1 && tile + gridDim.x < p.n_tiles) prefetch(P16 + lane, 32, (tile + gridDim.x) << 13);
                 round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
             }
             // ---- STAGE 12 between the parked lower half and the registers; coalesced stores ----
@@ -191,12 +193,12 @@ __global__ void __launch_bounds__(256, 2) fast32_n13_kernel(const __grid_constan
                     for (int m = 0; m < 16; ++m) { const int2 v = S[m * 256 + tid]; re[m] = mk(v.x); im[m] = mk(v.y); }
                 }
                 round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
+                __syncthreads();                           // every warp is done with the previous half's A-side reads
 #pragma unroll
                 for (int m = 0; m < 16; ++m) Q[pC + 288u * m] = make_int2(re[m].f, im[m].f);
                 __syncthreads();
 #pragma unroll
                 for (int m = 0; m < 16; ++m) { const int2 v = Q[pB + 18u * m]; re[m] = mk(v.x); im[m] = mk(v.y); }
-                __syncthreads();
                 round32<4, DIT, MODE, KIND>(re, im, p, 4, TwSmem32{midtw + (tid & 15u), 16}, false, false);
                 __syncwarp();
 #pragma unroll

@@ -50,8 +50,9 @@ int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const 
     }
     long long grid = 2ll * num_sms;
     int e = (int)cudaErrorInvalidValue;
-    if (pd.kp.c == 0 && pd.kp.g == 13) {               // one-pass 8192-point kernel: two 256-thread CTAs per SM
+    if (pd.kp.c == 0 && pd.kp.g == 13) {               // one-pass 8192-point kernel
         p.n_tiles = pd.kp.total >> 13;
+        grid = 3ll * num_sms;                          // 80 registers, 70 KB of shared memory: three CTAs per SM
         if (grid > p.n_tiles) grid = p.n_tiles;
         if (grid < 1) grid = 1;
         e = f32_launch_n13(p, dit, mode, kind, (int)grid, stream);
