@@ -297,7 +297,20 @@ __global__ void __launch_bounds__(256, 2) fast64_kernel(const __grid_constant__ 
         }
         if (DIT) round64<4, DIT, MODE, KIND>(re, im, p, uwr, uwi);
         else round64<0, DIT, MODE, KIND>(re, im, p, lwr, lwi);
-        if (active) {
+        if (!DIT && p.out_sb == 8) {
+            // DIF leaves 16 contiguous samples (256 bytes) in each lane: stored directly, one instruction
+            // would touch 32 different lines.  The lane's own tile slots (the ones it read for this
+            // round) take the results in place, and the warp then writes 512 contiguous bytes per
+            // instruction.
+#pragma unroll
+            for (int m = 0; m < 16; ++m) sm[pB + m] = make_longlong2(re[m], im[m]);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const longlong2 v = sm[phys64(lane) + 34u * j];          // phys64(lane + 32 j)
+                if (g0 + lane + 32u * j < p.total) reinterpret_cast<longlong2 *>(p.out)[g0 + lane + 32u * j] = v;
+            }
+        } else if (active) {
             if (p.out_sb == 8) {
 #pragma unroll
                 for (int m = 0; m < 16; ++m)
