@@ -300,12 +300,24 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
     constexpr int LOF = RF == 0 ? 0 : R0 + 4 * (RF - 1);
     constexpr int RRF = RF == 0 ? R0 : 4;
     const unsigned basef = (tid & ((1u << LOF) - 1u)) | ((tid >> LOF) << (LOF + RRF));
+    // DIT with a 4-stage first round reads 16 contiguous samples per thread: those travel as 16-byte pieces
+    // into slots [piece][tid] (8 pieces of two samples, or 4 pieces of four packed 16-bit samples)
+    constexpr bool PIECES = DIT && R0 == 4;
     auto prefetch = [&](long long t) {
         const char *src = reinterpret_cast<const char *>(p.in) + ((t << 12) + basef) * esz;
+        if (PIECES) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            const unsigned off = ((unsigned)(m & ((1 << RRF) - 1)) << LOF) | ((unsigned)(m >> RRF) << (8 + RRF));
-            cp_async_elem(stage + (m * 256 + tid) * esz, src + (long long)off * esz, esz);
+            for (int j = 0; j < 8; ++j)
+                if (j < esz) {
+                    const unsigned d = (unsigned)__cvta_generic_to_shared(stage + (j * 256 + tid) * 16);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 16 * j) : "memory");
+                }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const unsigned off = ((unsigned)(m & ((1 << RRF) - 1)) << LOF) | ((unsigned)(m >> RRF) << (8 + RRF));
+                cp_async_elem(stage + (m * 256 + tid) * esz, src + (long long)off * esz, esz);
+            }
         }
         cp_async_commit();
     };
@@ -357,13 +369,39 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
 
             if (first && staged) {                    // this tile was prefetched into the thread's slots
                 cp_async_wait_all();
+                if (PIECES) {
+                    const int4 *st16 = reinterpret_cast<const int4 *>(stage);
+                    int a[16], b[16];
+                    if (p.in_sb == 4) {
 #pragma unroll
-                for (int m = 0; m < 16; ++m) {
-                    int a, b;
-                    stage_read(stage, tid, m, p.in_sb, a, b);
-                    if (p.in_wrap) { a = sx(a, p.dw); b = sx(b, p.dw); }
-                    re[m] = mk(a);
-                    im[m] = mk(b);
+                        for (int j = 0; j < 8; ++j) {
+                            const int4 v = st16[j * 256 + tid];
+                            a[2 * j] = v.x; b[2 * j] = v.y; a[2 * j + 1] = v.z; b[2 * j + 1] = v.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int4 v = st16[j * 256 + tid];
+                            const int x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { a[4 * j + e] = (int)(short)(x[e] & 0xffff); b[4 * j + e] = x[e] >> 16; }
+                        }
+                    }
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        if (p.in_wrap) { a[m] = sx(a[m], p.dw); b[m] = sx(b[m], p.dw); }
+                        re[m] = mk(a[m]);
+                        im[m] = mk(b[m]);
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        int a, b;
+                        stage_read(stage, tid, m, p.in_sb, a, b);
+                        if (p.in_wrap) { a = sx(a, p.dw); b = sx(b, p.dw); }
+                        re[m] = mk(a);
+                        im[m] = mk(b);
+                    }
                 }
                 const long long nt = tile + gridDim.x;    // refill the slots with this CTA's next tile
                 staged = nt < p.n_tiles && ((nt + 1) << 12) <= p.total;
@@ -392,7 +430,22 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
             else if (r == 1) round32<4, DIT, MODE, KIND>(re, im, p, R0, TwSmem32{midtw + (tid & ((1u << R0) - 1u)), 1 << R0}, false, tid_odd);
             else round32<4, DIT, MODE, KIND>(re, im, p, R0 + 4, TwRegs32{uwr, uwi}, false, tid_odd);
 
-            if (last && full) {
+            if (last && full && !DIT && R0 == 4 && p.out_sb == 4) {
+                // DIF ends with 16 contiguous samples (128 bytes) per thread; stored directly, one instruction
+                // would touch 32 lines.  The thread's own tile slots take the results in place (the
+                // preceding hand-over was warp-local, so the warp owns these 512 samples), then the warp
+                // writes 512 contiguous bytes per instruction.
+#pragma unroll
+                for (int m = 0; m < 16; ++m) sm[pbase + m] = make_int2(re[m].f, im[m].f);
+                __syncwarp();
+                const unsigned w0 = (tid & ~31u) << 4, lane = tid & 31u;
+                int4 *dst = reinterpret_cast<int4 *>(reinterpret_cast<int2 *>(p.out) + g0 + w0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned i = w0 + 2u * lane + 64u * j;
+                    dst[lane + 32 * j] = *reinterpret_cast<const int4 *>(sm + phys8(i));
+                }
+            } else if (last && full) {
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
                     const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));

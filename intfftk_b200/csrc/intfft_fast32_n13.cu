@@ -208,9 +208,16 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
                 for (int m = 0; m < 16; ++m) { const int2 v = P[pA + m]; re[m] = mk(v.x); im[m] = mk(v.y); }
                 round32<4, DIT, MODE, KIND>(re, im, p, 0, TwRegs32{lwr, lwi}, true, false);
                 if (p.out_sb == 4) {
-                    int4 *dst = reinterpret_cast<int4 *>(p.out) + ((gh + 16u * tid) >> 1);
+                    // 16 contiguous samples (128 bytes) per thread: back into the thread's own tile slots, then
+                    // the warp (which owns these 512 samples) writes 512 contiguous bytes per instruction
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_int4(re[2 * j].f, im[2 * j].f, re[2 * j + 1].f, im[2 * j + 1].f);
+                    for (int m = 0; m < 16; ++m) P[pA + m] = make_int2(re[m].f, im[m].f);
+                    __syncwarp();
+                    const unsigned w0 = (tid & ~31u) << 4;
+                    int4 *dst = reinterpret_cast<int4 *>(reinterpret_cast<int2 *>(p.out) + gh + w0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dst[lane + 32 * j] = *reinterpret_cast<const int4 *>(P + phys8(w0 + 2u * lane + 64u * j));
                 } else {
                     uint4 *dst = reinterpret_cast<uint4 *>(p.out) + ((gh + 16u * tid) >> 2);
 #pragma unroll

@@ -45,6 +45,14 @@ def others():
     time_plan(65536, steps=5, NFFT=12, DATA_WIDTH=16, FORMAT=0, RNDMODE=1)
     time_plan(65536, steps=5, NFFT=12, DATA_WIDTH=16, FORMAT=1)
 
+def extra():
+    time_plan(131072, steps=5, direction=0, NFFT=13, DATA_WIDTH=18, FORMAT=0)
+    time_plan(65536, steps=5, direction=1, NFFT=12, DATA_WIDTH=18, FORMAT=0)
+    time_plan(65536, steps=5, direction=0, NFFT=12, DATA_WIDTH=18, FORMAT=0)
+    time_plan(4096, steps=5, direction=1, NFFT=16, DATA_WIDTH=16, FORMAT=0)
+    time_plan(4096, steps=5, direction=1, NFFT=16, DATA_WIDTH=24, FORMAT=0)
+    time_plan(4096, steps=5, direction=0, NFFT=16, DATA_WIDTH=24, FORMAT=0)
+
 def c3():
     time_plan(4096, steps=10, NFFT=16, DATA_WIDTH=24, FORMAT=1)
 
