@@ -652,6 +652,6 @@ template <int G, bool DIT> cudaError_t launch_strided(const Fast32Params &p, int
 int f32_launch_contig_dif(const f32::Fast32Params &p, int bits, int mode, int kind, int grid, void *stream);
 int f32_launch_contig_dit(const f32::Fast32Params &p, int bits, int mode, int kind, int grid, void *stream);
 int f32_launch_strided(const f32::Fast32Params &p, int g, bool dit, int mode, int kind, int grid, void *stream);
-int f32_launch_n13(const f32::Fast32Params &p, bool dit, int mode, int kind, int grid, void *stream);   // intfft_fast32_n13.cu
+int f32_launch_n13(const f32::Fast32Params &p, bool dit, int mode, int kind, int klo, int grid, void *stream);   // intfft_fast32_n13.cu
 
 }  // namespace intfft

@@ -32,7 +32,9 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
 constexpr int kCtas13 = 3;
 constexpr unsigned kSmem13 = kHead32 + kTile8 * 8 + 16 * 256 * 8;   // table + exchange tile + private slots (70 KB: 3 CTAs / SM)
 
-template <bool DIT, int MODE, int KIND>
+// KIND = multiplier-arrangement policy of STAGE 8..12, KLO = of STAGE 0..7 (UNSCALED plans grow past the
+// single-DSP limit only in their late stages: c5u runs STAGE 2..9 on the cheaper single-arrangement code)
+template <bool DIT, int MODE, int KIND, int KLO>
 __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_constant__ Fast32Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -151,14 +153,14 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
                     }
                 }
                 if (h == 0) prefetch(S16 + tid, 256, g0 + 4096);
-                round32<4, DIT, MODE, KIND>(re, im, p, 0, TwRegs32{lwr, lwi}, true, false);
+                round32<4, DIT, MODE, KLO>(re, im, p, 0, TwRegs32{lwr, lwi}, true, false);
                 __syncwarp();
 #pragma unroll
                 for (int m = 0; m < 16; ++m) P[pA + m] = make_int2(re[m].f, im[m].f);
                 __syncwarp();
 #pragma unroll
                 for (int m = 0; m < 16; ++m) { const int2 v = P[pB + 18u * m]; re[m] = mk(v.x); im[m] = mk(v.y); }
-                round32<4, DIT, MODE, KIND>(re, im, p, 4, TwSmem32{midtw + (tid & 15u), 16}, false, false);
+                round32<4, DIT, MODE, KLO>(re, im, p, 4, TwSmem32{midtw + (tid & 15u), 16}, false, false);
 #pragma unroll
                 for (int m = 0; m < 16; ++m) Q[pB + 18u * m] = make_int2(re[m].f, im[m].f);
                 __syncthreads();
@@ -199,14 +201,14 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
                 __syncthreads();
 #pragma unroll
                 for (int m = 0; m < 16; ++m) { const int2 v = Q[pB + 18u * m]; re[m] = mk(v.x); im[m] = mk(v.y); }
-                round32<4, DIT, MODE, KIND>(re, im, p, 4, TwSmem32{midtw + (tid & 15u), 16}, false, false);
+                round32<4, DIT, MODE, KLO>(re, im, p, 4, TwSmem32{midtw + (tid & 15u), 16}, false, false);
                 __syncwarp();
 #pragma unroll
                 for (int m = 0; m < 16; ++m) P[pB + 18u * m] = make_int2(re[m].f, im[m].f);
                 __syncwarp();
 #pragma unroll
                 for (int m = 0; m < 16; ++m) { const int2 v = P[pA + m]; re[m] = mk(v.x); im[m] = mk(v.y); }
-                round32<4, DIT, MODE, KIND>(re, im, p, 0, TwRegs32{lwr, lwi}, true, false);
+                round32<4, DIT, MODE, KLO>(re, im, p, 0, TwRegs32{lwr, lwi}, true, false);
                 if (p.out_sb == 4) {
                     // 16 contiguous samples (128 bytes) per thread: back into the thread's own tile slots, then
                     // the warp (which owns these 512 samples) writes 512 contiguous bytes per instruction
@@ -241,24 +243,31 @@ template <typename K> cudaError_t launch_n13(K k, const Fast32Params &p, int gri
     return cudaGetLastError();
 }
 
-template <bool DIT> cudaError_t launch_n13_dir(const Fast32Params &p, int mode, int kind, int grid, cudaStream_t st)
+template <bool DIT> cudaError_t launch_n13_dir(const Fast32Params &p, int mode, int kind, int klo, int grid, cudaStream_t st)
 {
-    switch (mode * 2 + kind) {
-    case MODE_TRUNC * 2 + 0: return launch_n13(fast32_n13_kernel<DIT, MODE_TRUNC, KIND_SINGLE>, p, grid, st);
-    case MODE_TRUNC * 2 + 1: return launch_n13(fast32_n13_kernel<DIT, MODE_TRUNC, KIND_MIXED>, p, grid, st);
-    case MODE_ROUND * 2 + 0: return launch_n13(fast32_n13_kernel<DIT, MODE_ROUND, KIND_SINGLE>, p, grid, st);
-    case MODE_ROUND * 2 + 1: return launch_n13(fast32_n13_kernel<DIT, MODE_ROUND, KIND_MIXED>, p, grid, st);
-    case MODE_UNSCALED * 2 + 0: return launch_n13(fast32_n13_kernel<DIT, MODE_UNSCALED, KIND_SINGLE>, p, grid, st);
-    default: return launch_n13(fast32_n13_kernel<DIT, MODE_UNSCALED, KIND_MIXED>, p, grid, st);
+    constexpr int S = KIND_SINGLE, M = KIND_MIXED;
+    switch (mode * 4 + kind * 2 + klo) {
+    case MODE_TRUNC * 4 + 0: return launch_n13(fast32_n13_kernel<DIT, MODE_TRUNC, S, S>, p, grid, st);
+    case MODE_TRUNC * 4 + 2: return launch_n13(fast32_n13_kernel<DIT, MODE_TRUNC, M, S>, p, grid, st);
+    case MODE_TRUNC * 4 + 3: return launch_n13(fast32_n13_kernel<DIT, MODE_TRUNC, M, M>, p, grid, st);
+    case MODE_ROUND * 4 + 0: return launch_n13(fast32_n13_kernel<DIT, MODE_ROUND, S, S>, p, grid, st);
+    case MODE_ROUND * 4 + 2: return launch_n13(fast32_n13_kernel<DIT, MODE_ROUND, M, S>, p, grid, st);
+    case MODE_ROUND * 4 + 3: return launch_n13(fast32_n13_kernel<DIT, MODE_ROUND, M, M>, p, grid, st);
+    case MODE_UNSCALED * 4 + 0: return launch_n13(fast32_n13_kernel<DIT, MODE_UNSCALED, S, S>, p, grid, st);
+    case MODE_UNSCALED * 4 + 2: return launch_n13(fast32_n13_kernel<DIT, MODE_UNSCALED, M, S>, p, grid, st);
+    case MODE_UNSCALED * 4 + 3: return launch_n13(fast32_n13_kernel<DIT, MODE_UNSCALED, M, M>, p, grid, st);
+    default: return cudaErrorInvalidValue;          // single late stages with double early ones: fall back below
     }
 }
 
 }  // namespace f32
 
-int f32_launch_n13(const f32::Fast32Params &p, bool dit, int mode, int kind, int grid, void *stream)
+// kind / klo: arrangement policy of STAGE 8..12 / STAGE 0..7 (KIND_SINGLE or KIND_MIXED)
+int f32_launch_n13(const f32::Fast32Params &p, bool dit, int mode, int kind, int klo, int grid, void *stream)
 {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    return (int)(dit ? f32::launch_n13_dir<true>(p, mode, kind, grid, st) : f32::launch_n13_dir<false>(p, mode, kind, grid, st));
+    if (klo == f32::KIND_MIXED) kind = f32::KIND_MIXED;     // (single, mixed) is not instantiated: mixed covers it
+    return (int)(dit ? f32::launch_n13_dir<true>(p, mode, kind, klo, grid, st) : f32::launch_n13_dir<false>(p, mode, kind, klo, grid, st));
 }
 
 }  // namespace intfft

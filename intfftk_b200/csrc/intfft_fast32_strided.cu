@@ -38,14 +38,17 @@ int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const 
     p.cm = pd.kp.cm;
     for (int i = 0; i < 16; ++i) { p.lw_r[i] = lw_r[i]; p.lw_i[i] = lw_i[i]; }
     // multiplier arrangement policy: all stages of this pass single-DSP, or decided per stage
-    int kind = f32::KIND_SINGLE;
+    int kind = f32::KIND_SINGLE, kind_lo = f32::KIND_SINGLE;     // kind_lo: the same question for STAGE < 8 only
     {
         const int n = pd.kp.n, fmt = pd.kp.format;
         for (int b = pd.kp.pb; b < pd.kp.pb + pd.kp.g; ++b) {
             const int ii = dit ? b : n - 1 - b;
             const int dtw = pd.kp.dw + ii * fmt;
             const int dtwc = dit ? dtw : dtw + fmt;
-            if (b >= 2 && dtwc >= pd.kp.cm.lim_single) kind = f32::KIND_MIXED;
+            if (b >= 2 && dtwc >= pd.kp.cm.lim_single) {
+                kind = f32::KIND_MIXED;
+                if (b < 8) kind_lo = f32::KIND_MIXED;
+            }
         }
     }
     long long grid = 2ll * num_sms;
@@ -55,7 +58,7 @@ int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const 
         grid = 3ll * num_sms;                          // 80 registers, 70 KB of shared memory: three CTAs per SM
         if (grid > p.n_tiles) grid = p.n_tiles;
         if (grid < 1) grid = 1;
-        e = f32_launch_n13(p, dit, mode, kind, (int)grid, stream);
+        e = f32_launch_n13(p, dit, mode, kind, kind_lo, (int)grid, stream);
     } else if (pd.kp.c == 0) {
         if (grid > p.n_tiles) grid = p.n_tiles;
         if (grid < 1) grid = 1;
