@@ -98,6 +98,58 @@ __global__ void bitrev_kernel(const E *in, E *out, int n, int h, long long n_til
     }
 }
 
+// Same permutation with 16-byte global accesses: a 2^h x 2^h tile (h = 6 for NFFT >= 12) is read as
+// 16-byte vectors along its rows (runs of 2^h consecutive samples), parked element-wise in a padded
+// shared tile, and written as 16-byte vectors along the rows of the transposed, index-reversed tile.
+// 256 threads move 4096 samples per trip, so every thread keeps 64..256 bytes in flight.
+template <typename E>
+__global__ void __launch_bounds__(256) bitrev_vec_kernel(const E *in, E *out, int n, int h, long long n_tiles)
+{
+    constexpr int V = 16 / (int)sizeof(E);          // elements per 16-byte vector: 4 / 2 / 1
+    union Vec { uint4 q; E e[V]; };
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    E *tile = reinterpret_cast<E *>(smem_raw);
+    const int side = 1 << h, pitch = side + 1;
+    const int vpr_log2 = h - (V == 4 ? 2 : (V == 2 ? 1 : 0));     // log2 vectors per row
+    const int n_vec = side << vpr_log2;
+    const int mid_bits = n - 2 * h;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const unsigned mid = (unsigned)(t & ((1ll << mid_bits) - 1));
+        const long long frame = t >> mid_bits;
+        const E *src = in + (frame << n) + ((long long)mid << h);
+        for (int v = threadIdx.x; v < n_vec; v += blockDim.x) {
+            const int row = v >> vpr_log2, c0 = (v & ((1 << vpr_log2) - 1)) * V;
+            Vec x;
+            x.q = __ldg(reinterpret_cast<const uint4 *>(src + ((long long)row << (n - h)) + c0));
+#pragma unroll
+            for (int e = 0; e < V; ++e) tile[row * pitch + c0 + e] = x.e[e];
+        }
+        __syncthreads();
+        E *dst = out + (frame << n) + ((long long)rev_bits(mid, mid_bits) << h);
+        for (int v = threadIdx.x; v < n_vec; v += blockDim.x) {
+            const int row = v >> vpr_log2, c0 = (v & ((1 << vpr_log2) - 1)) * V;
+            const unsigned s_col = rev_bits((unsigned)row, h);
+            Vec x;
+#pragma unroll
+            for (int e = 0; e < V; ++e) x.e[e] = tile[rev_bits((unsigned)(c0 + e), h) * pitch + s_col];
+            *reinterpret_cast<uint4 *>(dst + ((long long)row << (n - h)) + c0) = x.q;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename E>
+cudaError_t launch_bitrev_vec(const void *in, void *out, int n, int h, long long n_tiles, cudaStream_t st)
+{
+    const int side = 1 << h;
+    const size_t smem = (size_t)side * (side + 1) * sizeof(E);
+    cudaError_t e = cudaFuncSetAttribute(bitrev_vec_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long grid = n_tiles < 148 * 8 ? n_tiles : 148 * 8;
+    bitrev_vec_kernel<E><<<(int)grid, 256, smem, st>>>((const E *)in, (E *)out, n, h, n_tiles);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -134,6 +186,18 @@ int launch_checksum(const void *buf, long long n_scalars, int sb, uint64_t *d_su
 
 int launch_bitrev(int n, int sb, long long batch, const void *in, void *out, void *stream)
 {
+    // 16-byte path: rows of 2^h samples must hold whole, aligned vectors
+    const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    if (aligned && n >= 8) {
+        const int hv = n / 2 < 6 ? n / 2 : 6;
+        const long long tiles = batch << (n - 2 * hv);
+        cudaStream_t sv = (cudaStream_t)stream;
+        cudaError_t e = sb == 2 ? launch_bitrev_vec<short2>(in, out, n, hv, tiles, sv)
+                      : sb == 4 ? launch_bitrev_vec<int2>(in, out, n, hv, tiles, sv)
+                                : launch_bitrev_vec<longlong2>(in, out, n, hv, tiles, sv);
+        count_launch();
+        return (int)e;
+    }
     const int h = n / 2 < 5 ? n / 2 : 5;
     const int side = 1 << h;
     const long long n_tiles = batch << (n - 2 * h);

@@ -53,6 +53,36 @@ def extra():
     time_plan(4096, steps=5, direction=1, NFFT=16, DATA_WIDTH=24, FORMAT=0)
     time_plan(4096, steps=5, direction=0, NFFT=16, DATA_WIDTH=24, FORMAT=0)
 
+def timeit(fn, steps=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+def f12():
+    """f1 (natural-order wrapper) and f2 (FFT -> IFFT pair) at the c2 shape"""
+    for direction in (0, 1):
+        g = ib.Generics(NFFT=12, DATA_WIDTH=16, FORMAT=0)
+        core = ib.Core(g, 65536, direction)
+        x, y = core.new_input(), core.new_output()
+        ib.fill_random(x, 16, 1)
+        print(f"exec_natural c2 dir={direction}: {timeit(lambda: core.exec_natural(x, y))*1e3:8.1f} us   (exec alone {timeit(lambda: core.exec(x, y))*1e3:8.1f} us)", flush=True)
+        core.close()
+    z = torch.empty_like(x)
+    print(f"bitrev_order alone (2^28 x 4 B): {timeit(lambda: ib.bitrev_order(x, 12, z))*1e3:8.1f} us", flush=True)
+    pair = ib.Pair(ib.Generics(NFFT=12, DATA_WIDTH=16, FORMAT=0), 65536)
+    print(f"pair c2: {timeit(lambda: pair.exec(x, y))*1e3:8.1f} us", flush=True)
+    pair.close()
+    g = ib.Generics(NFFT=13, DATA_WIDTH=18, FORMAT=0)
+    core = ib.Core(g, 131072, 1)
+    x, y = core.new_input(), core.new_output()
+    ib.fill_random(x, 18, 1)
+    print(f"exec_natural c5: {timeit(lambda: core.exec_natural(x, y), 5)*1e3:8.1f} us   (exec alone {timeit(lambda: core.exec(x, y), 5)*1e3:8.1f} us)", flush=True)
+    core.close()
+
 def c3():
     time_plan(4096, steps=10, NFFT=16, DATA_WIDTH=24, FORMAT=1)
 
