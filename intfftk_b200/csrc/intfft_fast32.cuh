@@ -98,11 +98,17 @@ __device__ __forceinline__ long long mulw(int a, int b)
     return r;
 }
 // t >> k for 0 <= k < 32 (every pre-shift of the double arrangements is below 32)
+// (register pairs are split / joined with mov.b64: built from shifts and ORs, the front end no longer sees
+// a plain pair and turns every 64-bit add that follows into five or six instructions)
 __device__ __forceinline__ long long sra64(long long t, int k)
 {
-    const unsigned lo = __funnelshift_r((unsigned)t, (unsigned)(t >> 32), k);
-    const int hi = (int)(t >> 32) >> k;
-    return (long long)(((unsigned long long)(unsigned)hi << 32) | lo);
+    unsigned lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(t));
+    const unsigned rlo = __funnelshift_r(lo, hi, k);
+    const int rhi = (int)hi >> k;
+    long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(rlo), "r"(rhi));
+    return r;
 }
 
 template <int MODE, int KIND>
