@@ -375,6 +375,19 @@ def test_bitrev_order(ib, oracle, nfft):
         assert np.array_equal(got, oracle.bitrev(nfft, x))
 
 
+def test_bitrev_order_unaligned_buffers_take_the_scalar_path(ib, oracle):
+    """The 16-byte reorder kernel needs 16-byte-aligned buffers; anything else must still be reordered."""
+    nfft, batch = 12, 3
+    n = 1 << nfft
+    x = np.arange(batch * n * 2, dtype=np.int64).astype(np.int16).reshape(batch, n, 2)
+    pad = torch.zeros(batch * n * 2 + 2, dtype=torch.int16, device="cuda")
+    src = pad[2:]                                   # 4 bytes past a 256-byte-aligned allocation
+    src.copy_(torch.from_numpy(x).reshape(-1))
+    assert src.data_ptr() % 16 == 4
+    got = ib.bitrev_order(src, nfft).cpu().numpy().reshape(batch, n, 2)
+    assert np.array_equal(got, oracle.bitrev(nfft, x))
+
+
 def test_fft_ifft_pair_roundtrip_full_c2_batch(ib, oracle):
     """Size-independent property at the full c2 size (65536 x 4096): FFT then IFFT returns x / N
     within the truncation bias; plus a checksum-of-frames comparison with the oracle on a sample."""
