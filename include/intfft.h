@@ -86,7 +86,9 @@ int intfft_query(const intfft_plan *p, intfft_layout *l);
 
 /* Run `batch` frames. d_in / d_out are DEVICE pointers in the flat layout above; asynchronous on
  * `cuda_stream` (a cudaStream_t, NULL = default stream). d_in == d_out is allowed when the input
- * and output containers have the same size. Replaces driving DI_RE0/IM0/RE1/IM1 + DI_ENA and
+ * and output containers have the same size. Both pointers must be 16-byte aligned (the kernels move
+ * frames with 16-byte vector and TMA bulk accesses; cudaMalloc memory and any whole-frame offset into
+ * it qualify), otherwise INTFFT_EINVAL. Replaces driving DI_RE0/IM0/RE1/IM1 + DI_ENA and
  * sampling DO_* + DO_VAL (int_fftNk.vhd:86-102). */
 int intfft_exec(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream);
 

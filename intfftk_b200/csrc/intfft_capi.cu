@@ -318,6 +318,7 @@ int intfft_exec(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream
 {
     if (!p || !d_in || !d_out) return INTFFT_EINVAL;
     if (d_in == d_out && p->in_sb != p->out_sb) return INTFFT_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15u) return INTFFT_EINVAL;
     DeviceGuard guard(p->device);
     if (!guard.ok) return INTFFT_ECUDA;
     return exec_frames(p, d_in, d_out, p->batch, cuda_stream);
@@ -326,6 +327,7 @@ int intfft_exec(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream
 int intfft_exec_natural(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream)
 {
     if (!p || !d_in || !d_out || d_in == d_out) return INTFFT_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15u) return INTFFT_EINVAL;
     DeviceGuard guard(p->device);
     if (!guard.ok) return INTFFT_ECUDA;
     intfft_layout l;

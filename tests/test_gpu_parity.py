@@ -375,6 +375,15 @@ def test_bitrev_order(ib, oracle, nfft):
         assert np.array_equal(got, oracle.bitrev(nfft, x))
 
 
+def test_exec_rejects_misaligned_device_buffers(ib):
+    g = ib.Generics(NFFT=8, DATA_WIDTH=16, FORMAT=0)
+    core = ib.Core(g, 2, 0)
+    pad = torch.zeros(2 * 256 * 2 + 2, dtype=torch.int16, device="cuda")
+    with pytest.raises(ib.IntfftError):
+        core.exec(pad[2:], core.new_output())
+    core.close()
+
+
 def test_bitrev_order_unaligned_buffers_take_the_scalar_path(ib, oracle):
     """The 16-byte reorder kernel needs 16-byte-aligned buffers; anything else must still be reordered."""
     nfft, batch = 12, 3
