@@ -334,9 +334,16 @@ int intfft_exec_natural(intfft_plan *p, const void *d_in, void *d_out, void *cud
     intfft_query(p, &l);
     const bool dit = p->g.direction != 0;
     // the reorder acts on the bit-reversed side: the FFT's output / the IFFT's input
+    const int n = p->g.nfft_log2;
+    // a 4096-point packed-16 FFT reorders inside its own kernel (natural-order stores): no second pass
+    if (!dit && p->g.use_fly && p->passes.size() == 1 && p->passes[0].path == 1 && p->passes[0].kp.g == 12) {
+        p->passes[0].natural = 1;
+        const int st = exec_frames(p, d_in, d_out, p->batch, cuda_stream);
+        p->passes[0].natural = 0;
+        return st;
+    }
     const size_t need = (size_t)(dit ? l.in_bytes : l.out_bytes);
     if (!p->nat && cudaMalloc(&p->nat, need) != cudaSuccess) return INTFFT_ENOMEM;
-    const int n = p->g.nfft_log2;
     if (!dit) {
         const int st = exec_frames(p, d_in, p->nat, p->batch, cuda_stream);
         if (st) return st;

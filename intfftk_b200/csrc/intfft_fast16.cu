@@ -215,9 +215,18 @@ struct TwSmem {          // table[w][tid & 15] of pre-shifted (re, im); one LDS.
 
 // MIDSM: keep the middle round's 15 twiddles in a 1920-byte shared table instead of 30 registers, which
 // brings the kernel under 85 registers so that three CTAs (24 warps) fit on one SM.
-template <int NLOG2, bool DIT, bool DW16, bool MIDSM, int MODE>
+// NAT (4096-point DIF only): int_bitrev_order (buffers/int_bitrev_order.vhd:82-104) fused into the output.
+// After the last round a thread holds in-place positions q = 16 tid + m; their natural positions
+// rev12(q) = rev4(m) << 8 | rev8(tid) are scattered into the tile's (by then dead) TMA landing buffer,
+// whose 16-byte chunks are XOR-swizzled by address bits 5..7 so that the scatter is 4-way instead of
+// 8-way bank-conflicted, and after one CTA barrier the frame leaves as 16-byte stores in natural order.
+// The landing buffer of the NEXT tile doubles as the previous tile's scatter buffer, so in this variant
+// the TMA prefetch is issued after the tile's first CTA barrier (every thread has then left the
+// previous tile) instead of at the top of the tile.
+template <int NLOG2, bool DIT, bool DW16, bool MIDSM, int MODE, bool NAT = false>
 __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid_constant__ Fast16Params p)
 {
+    static_assert(!NAT || (NLOG2 == 12 && !DIT), "fused natural-order output: 4096-point DIF only");
     constexpr int R0 = ((NLOG2 - 1) % 4) + 1;      // stages in the lowest round
     constexpr int NR = 1 + (NLOG2 - R0) / 4;       // rounds; round r > 0 covers bits R0+4(r-1) .. +3
     static_assert(NR >= 2 && NR <= 3, "supported: 2^5 .. 2^12 points");
@@ -287,14 +296,18 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
         const long long g0 = tile << 12;
         const bool full = g0 + 4096 <= p.total;
 
-        if (TMA_IN) {
-            const long long nt = tile + gridDim.x;            // prefetch the next frame of this CTA
+        auto prefetch_next = [&]() {                          // the next frame of this CTA
+            const long long nt = tile + gridDim.x;
             if (tid == 0 && nt < p.n_tiles) {
                 const long long left = p.total - (nt << 12);
                 const uint32_t bytes = (uint32_t)(left < 4096 ? left : 4096) * 4u;
+                if (NAT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> TMA writes
                 mbar_expect_tx(&bar[(it + 1) & 1], bytes);
                 tma_load_1d(stage[(it + 1) & 1], p.in + (nt << 12), bytes, &bar[(it + 1) & 1]);
             }
+        };
+        if (TMA_IN) {
+            if (!NAT) prefetch_next();
             mbar_wait(&bar[it & 1], (it >> 1) & 1);
         }
 
@@ -351,7 +364,16 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                 for (int c = 0; c < 4; ++c) {
                     const uint4 v = make_uint4(pack(re[4 * c], im[4 * c]), pack(re[4 * c + 1], im[4 * c + 1]),
                                                pack(re[4 * c + 2], im[4 * c + 2]), pack(re[4 * c + 3], im[4 * c + 3]));
-                    if (last) {
+                    if (last && NAT) {
+                        const unsigned r8 = __brev(tid) >> 24;
+                        uint32_t *nb = stage[it & 1] + (r8 ^ (((r8 >> 5) & 7u) << 2));
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int m = 4 * c + e;
+                            nb[(((m & 1) << 3) | ((m & 2) << 1) | ((m & 4) >> 1) | ((m & 8) >> 3)) << 8] = w[e];
+                        }
+                    } else if (last) {
                         const long long gi = g0 + 16 * tid + 4 * c;
                         if (full || gi < p.total) *reinterpret_cast<uint4 *>(p.out + gi) = v;
                     } else {
@@ -375,6 +397,12 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                 const bool warp_local = (NR == 3 && R0 == 4) && ((DIT && rr == 0) || (!DIT && rr == 1));
                 if (warp_local) __syncwarp();
                 else __syncthreads();
+                if (NAT && rr == 0) prefetch_next();
+            } else if (NAT) {
+                __syncthreads();
+                const uint4 *nb = reinterpret_cast<const uint4 *>(stage[it & 1]) + (tid ^ ((tid >> 3) & 7u));
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(p.out + g0 + 4 * (tid + 256 * c)) = nb[256 * c];
             }
         }
     }
@@ -539,12 +567,12 @@ cudaError_t launch_strided_k(const Strided16Params &p, int mode, int grid, cudaS
     return cudaGetLastError();
 }
 
-template <int NLOG2, bool DIT, bool DW16>
+template <int NLOG2, bool DIT, bool DW16, bool NAT = false>
 cudaError_t launch_k(const Fast16Params &p, int mode, int grid, cudaStream_t st)
 {
     const int smem = kSmemHead + 2 * kTileWords * 4 + (DIT ? 0 : 2 * 4096 * 4);
     constexpr bool MIDSM = (NLOG2 == 12);
-    auto k = mode == MODE_ROUND ? fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_ROUND> : fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_TRUNC>;
+    auto k = mode == MODE_ROUND ? fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_ROUND, NAT> : fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_TRUNC, NAT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, smem, st>>>(p);
@@ -629,7 +657,10 @@ int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const
     case 9: e = launch_n<9>(p, mode, dit, dw16, (int)grid, st); break;
     case 10: e = launch_n<10>(p, mode, dit, dw16, (int)grid, st); break;
     case 11: e = launch_n<11>(p, mode, dit, dw16, (int)grid, st); break;
-    case 12: e = launch_n<12>(p, mode, dit, dw16, (int)grid, st); break;
+    case 12:
+        if (pd.natural && !dit) e = dw16 ? launch_k<12, false, true, true>(p, mode, (int)grid, st) : launch_k<12, false, false, true>(p, mode, (int)grid, st);
+        else e = launch_n<12>(p, mode, dit, dw16, (int)grid, st);
+        break;
     default: e = cudaErrorInvalidValue; break;
     }
     count_launch();

@@ -61,8 +61,8 @@ template <bool DIT, int MODE> __device__ __forceinline__ Stg64 stage64(const Fas
 
 // register pairs are split / joined with mov.b64: built from shifts and ORs, the front end no longer sees a
 // plain pair and spends five or six instructions on every 64-bit add that follows
-__device__ __forceinline__ unsigned lo32(int64_t v) { unsigned lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); return lo; }
-__device__ __forceinline__ int hi32(int64_t v) { unsigned lo; int hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ unsigned lo32(int64_t v) { unsigned lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); (void)hi; return lo; }
+__device__ __forceinline__ int hi32(int64_t v) { unsigned lo; int hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); (void)lo; return hi; }
 __device__ __forceinline__ int64_t mk64(unsigned lo, int hi) { int64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
 
 // d = hi * 2^32 + (int)lo with hi corrected for the sign of the low word

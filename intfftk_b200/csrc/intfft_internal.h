@@ -57,6 +57,7 @@ struct PassDesc {
     size_t smem_bytes;
     int scratch_in, scratch_out;  // -1 = user buffer, else index of plan scratch buffer
     int path;              // 0 generic tile kernel, 1 packed-16 kernels, 2 32-bit-lane kernels, 3 64-bit-lane low-8 kernel
+    int natural = 0;       // exec time: this (single, 4096-point packed-16 DIF) pass also applies int_bitrev_order
 };
 
 struct Plan {
