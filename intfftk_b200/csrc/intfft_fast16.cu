@@ -231,6 +231,9 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
     constexpr int NR = 1 + (NLOG2 - R0) / 4;       // rounds; round r > 0 covers bits R0+4(r-1) .. +3
     static_assert(NR >= 2 && NR <= 3, "supported: 2^5 .. 2^12 points");
     constexpr bool TMA_IN = !DIT;                  // DIF: first round reads stride-256 words -> stage via TMA
+    // DIF, 4-stage last round: results go back into the thread's own tile slots and leave warp-coalesced
+    // (stored directly, a warp instruction would write 32 separate 16-byte pieces at a 64-byte pitch)
+    constexpr bool COALESCE = !DIT && !NAT && R0 == 4 && NR == 3;
 
     static_assert(!MIDSM || (NR == 3 && R0 == 4), "MIDSM is for the three-round 4+4+4 schedule");
     // dynamic shared memory: [bar 2 x u64 | pad to 128] [mid twiddles 15 x 16 x int2] [work 2 x kTileWords]
@@ -373,6 +376,8 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                             const int m = 4 * c + e;
                             nb[(((m & 1) << 3) | ((m & 2) << 1) | ((m & 4) >> 1) | ((m & 8) >> 3)) << 8] = w[e];
                         }
+                    } else if (last && COALESCE) {
+                        *reinterpret_cast<uint4 *>(sm + pbase + phys(4 * c)) = v;       // in place: the slots this thread read
                     } else if (last) {
                         const long long gi = g0 + 16 * tid + 4 * c;
                         if (full || gi < p.total) *reinterpret_cast<uint4 *>(p.out + gi) = v;
@@ -398,6 +403,15 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                 if (warp_local) __syncwarp();
                 else __syncthreads();
                 if (NAT && rr == 0) prefetch_next();
+            } else if (COALESCE) {
+                // a warp owns 512 contiguous samples after the warp-local hand-over: 512 contiguous bytes per store
+                __syncwarp();
+                const unsigned w0 = (tid & ~31u) << 4, lane = tid & 31u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const unsigned i = w0 + 4u * lane + 128u * c;
+                    *reinterpret_cast<uint4 *>(p.out + g0 + i) = *reinterpret_cast<const uint4 *>(sm + phys(i));
+                }
             } else if (NAT) {
                 __syncthreads();
                 const uint4 *nb = reinterpret_cast<const uint4 *>(stage[it & 1]) + (tid ^ ((tid >> 3) & 7u));
