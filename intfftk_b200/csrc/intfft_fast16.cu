@@ -72,6 +72,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     } while (!ok);
 }
 
+// 16-byte piece with only the first `bytes` (0 or 16) read from global memory, the rest zero-filled
+__device__ __forceinline__ void cp_async_16z(void *smem_dst, const void *gsrc, unsigned bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_group0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <bool DW16>
 __device__ __forceinline__ void unpack(uint32_t x, int dw, int &re, int &im)
 {
@@ -234,6 +242,10 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
     // DIF, 4-stage last round: results go back into the thread's own tile slots and leave warp-coalesced
     // (stored directly, a warp instruction would write 32 separate 16-byte pieces at a 64-byte pitch)
     constexpr bool COALESCE = !DIT && !NAT && R0 == 4 && NR == 3;
+    // DIT, 4-stage first round: a thread needs its own 16 contiguous samples (64 bytes).  Loaded directly, a
+    // warp instruction would touch 32 separate 16-byte pieces at a 64-byte pitch, so the WARP fetches its
+    // 2 KB as 512 contiguous bytes per cp.async instruction into a skewed landing tile, one tile ahead.
+    constexpr bool CP_IN = DIT && R0 == 4;
 
     static_assert(!MIDSM || (NR == 3 && R0 == 4), "MIDSM is for the three-round 4+4+4 schedule");
     // dynamic shared memory: [bar 2 x u64 | pad to 128] [mid twiddles 15 x 16 x int2] [work 2 x kTileWords]
@@ -243,6 +255,7 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
     int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);
     uint32_t(*work)[kTileWords] = reinterpret_cast<uint32_t(*)[kTileWords]>(smem_raw + kSmemHead);
     uint32_t(*stage)[4096] = reinterpret_cast<uint32_t(*)[4096]>(smem_raw + kSmemHead + 2 * kTileWords * 4);
+    uint32_t *land = reinterpret_cast<uint32_t *>(smem_raw + kSmemHead + 2 * kTileWords * 4);     // CP_IN
 
     const unsigned tid = threadIdx.x;
     const int sh_full = p.sh_full, sh_half = p.sh_half;
@@ -263,6 +276,19 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
             tma_load_1d(stage[0], p.in + g0, bytes, &bar[0]);
         }
     }
+
+    auto prefetch_warp = [&](long long tile) {
+        const unsigned w0 = (tid & ~31u) << 4, lane = tid & 31u;
+        const long long g = (tile << 12) + w0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned i = 4u * lane + 128u * j;               // sample offset inside the warp's 512
+            const bool in_range = g + i < p.total;                  // p.total is a multiple of 4 samples
+            cp_async_16z(land + phys(w0 + i), in_range ? p.in + g + i : p.in, in_range ? 16u : 0u);
+        }
+        cp_async_commit_group();
+    };
+    if (CP_IN && (long long)blockIdx.x < p.n_tiles) prefetch_warp(blockIdx.x);
 
     // ---- per-thread constant twiddles of the upper rounds ----
     if (MIDSM) {                                   // table[w][lo4], w = (1 << q) - 1 + j, stage = R0 + q
@@ -326,12 +352,12 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
 
             // ---- fetch 16 samples ----
             if (r == 0 && R0 == 4) {
+                if (first && CP_IN) { cp_async_wait_group0(); __syncwarp(); }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint4 v;
-                    if (first) {                                  // DIT: straight from HBM, 64 B per thread
-                        const long long gi = g0 + 16 * tid + 4 * c;
-                        v = (full || gi < p.total) ? __ldg(reinterpret_cast<const uint4 *>(p.in + gi)) : make_uint4(0, 0, 0, 0);
+                    if (first) {                                  // DIT: this thread's 64 bytes of the landed tile
+                        v = *reinterpret_cast<const uint4 *>(land + pbase + phys(4 * c));
                     } else {
                         v = *reinterpret_cast<const uint4 *>(sm + pbase + phys(4 * c));
                     }
@@ -339,6 +365,10 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                     unpack<DW16>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
                     unpack<DW16>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
                     unpack<DW16>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                }
+                if (first && CP_IN) {                             // every lane has drained the warp's region
+                    __syncwarp();
+                    if (tile + gridDim.x < p.n_tiles) prefetch_warp(tile + gridDim.x);
                 }
             } else {
 #pragma unroll
@@ -584,7 +614,7 @@ cudaError_t launch_strided_k(const Strided16Params &p, int mode, int grid, cudaS
 template <int NLOG2, bool DIT, bool DW16, bool NAT = false>
 cudaError_t launch_k(const Fast16Params &p, int mode, int grid, cudaStream_t st)
 {
-    const int smem = kSmemHead + 2 * kTileWords * 4 + (DIT ? 0 : 2 * 4096 * 4);
+    const int smem = kSmemHead + 2 * kTileWords * 4 + (DIT ? (int)kTileWords * 4 : 2 * 4096 * 4);
     constexpr bool MIDSM = (NLOG2 == 12);
     auto k = mode == MODE_ROUND ? fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_ROUND, NAT> : fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_TRUNC, NAT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
