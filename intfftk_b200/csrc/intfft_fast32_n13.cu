@@ -30,10 +30,12 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
 }
 
 constexpr int kCtas13 = 3;
-constexpr unsigned kSmem13 = kHead32 + kTile8 * 8 + 16 * 256 * 8;   // table + exchange tile + private slots (70 KB: 3 CTAs / SM)
+constexpr unsigned kSmem13 = kHead32 + 2 * kTile8 * 8;   // table + exchange tile + slot tile (74 KB: 3 CTAs / SM)
 
 // KIND = multiplier-arrangement policy of STAGE 8..12, KLO = of STAGE 0..7 (UNSCALED plans grow past the
 // single-DSP limit only in their late stages: c5u runs STAGE 2..9 on the cheaper single-arrangement code)
+__device__ __forceinline__ unsigned pA_of(unsigned tid) { return phys8(16u * tid); }   // a thread's 16 contiguous tile slots
+
 template <bool DIT, int MODE, int KIND, int KLO>
 __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_constant__ Fast32Params p)
 {
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
     // will write as the A <-> B partner), so the only cross-warp hazards are the two guarded by CTA barriers
     int2 *P = reinterpret_cast<int2 *>(smem_raw + kHead32);                       // A <-> B (warp-local)
     int2 *Q = P;                                                                  // B <-> C
-    int2 *S = P + kTile8;                                                         // [16][256] private slots
+    int2 *S = P + kTile8;                                                         // thread-private slots (see below)
 
     const unsigned tid = threadIdx.x;
 
@@ -70,28 +72,35 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
     const int2 *twD = p.tw + (1u << 12) + tid;         // STAGE 12: index tid + 256 m (read through L1 / L2 per frame)
     __syncthreads();
 
-    const unsigned pA = phys8(16u * tid);
+    const unsigned pA = pA_of(tid);
     const unsigned pB = phys8((tid & 15u) | ((tid >> 4) << 8));
     const unsigned pC = phys8(tid);
     const Stg stD = stage_of<DIT, MODE, KIND>(p, 12);
 
-    // DIT: cp.async prefetch of one half's first-round input (16 contiguous samples per thread) as 16-byte
-    // pieces into slots dst[piece * pitch]; packed 16-bit input uses pieces 4..7 (see the swap above)
-    int4 *S16 = reinterpret_cast<int4 *>(S);
-    int4 *P16 = reinterpret_cast<int4 *>(P + 576u * (tid >> 5));                  // this warp's 512-sample region of P
-    const unsigned lane = tid & 31u;
-    auto prefetch = [&](int4 *dst, int pitch, long long first_sample) {
-        const char *src = reinterpret_cast<const char *>(p.in) + (first_sample + 16u * tid) * (2 * p.in_sb);
+    // DIT: a thread's first-round input is 16 contiguous samples.  Both tiles give every thread the eight
+    // 16-byte slots [pA, pA + 16) (tile-skewed, so LDS.128 / STS.128 on them are conflict-free); the WARP
+    // fetches its 512 samples as 512 contiguous bytes per cp.async instruction, piece k of the warp landing in
+    // the slot of the lane that owns it (packed 16-bit input: slots 4..7, so that parking the round-C results
+    // over slots 0..7 never overwrites a piece that is still unread).  Lower halves land in P, upper halves in S,
+    // where they trade places with the lower half's round-C results (which wait there for STAGE 12).
+    int4 *ownP = reinterpret_cast<int4 *>(P + pA_of(tid));
+    int4 *ownS = reinterpret_cast<int4 *>(S + pA_of(tid));
+    const unsigned lane = tid & 31u, w0 = (tid & ~31u) << 4;
+    // piece k = lane + 32 j: phys8 is additive over the disjoint bit fields, so every address is base + immediate
+    const unsigned land4 = phys8(w0 + 2u * lane);                                 // in_sb == 4: + 72 j  (int2 units)
+    const unsigned land2 = phys8(w0 + 16u * (lane >> 2)) + 8u + 2u * (lane & 3u); // in_sb == 2: + 144 j, slots 4..7
+    auto prefetch = [&](int2 *tile_base, long long first_sample) {
+        const char *src = reinterpret_cast<const char *>(p.in) + (first_sample + w0) * (2 * p.in_sb) + 16u * lane;
         if (p.in_sb == 4) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cp_async_16(dst + j * pitch, src + 16 * j);
+            for (int j = 0; j < 8; ++j) cp_async_16(tile_base + land4 + 72 * j, src + 512 * j);
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) cp_async_16(dst + (4 + j) * pitch, src + 16 * j);
+            for (int j = 0; j < 4; ++j) cp_async_16(tile_base + land2 + 144 * j, src + 512 * j);
         }
         cp_async_commit();
     };
-    if (DIT && (long long)blockIdx.x < p.n_tiles) prefetch(P16 + lane, 32, (long long)blockIdx.x << 13);
+    if (DIT && (long long)blockIdx.x < p.n_tiles) prefetch(P, (long long)blockIdx.x << 13);
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const long long g0 = tile << 13;
@@ -120,15 +129,16 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
                 // ---- lower half -> this warp's region of P, upper half -> S, where they now trade places with
                 // ---- the lower half's round-C results (which wait there for STAGE 12)
                 cp_async_wait_all();
+                __syncwarp();                              // the other lanes' pieces of this warp's region have landed too
                 if (p.in_sb == 4) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         int4 v;
                         if (h == 0) {
-                            v = P16[j * 32 + lane];
+                            v = ownP[j];
                         } else {
-                            v = S16[j * 256 + tid];
-                            S16[j * 256 + tid] = make_int4(re[2 * j].f, im[2 * j].f, re[2 * j + 1].f, im[2 * j + 1].f);
+                            v = ownS[j];
+                            ownS[j] = make_int4(re[2 * j].f, im[2 * j].f, re[2 * j + 1].f, im[2 * j + 1].f);
                         }
                         re[2 * j] = mk(sx(v.x, p.dw)); im[2 * j] = mk(sx(v.y, p.dw));
                         re[2 * j + 1] = mk(sx(v.z, p.dw)); im[2 * j + 1] = mk(sx(v.w, p.dw));
@@ -138,11 +148,11 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
                     for (int j = 0; j < 4; ++j) {
                         int4 v;
                         if (h == 0) {
-                            v = P16[(4 + j) * 32 + lane];
+                            v = ownP[4 + j];
                         } else {
-                            v = S16[(4 + j) * 256 + tid];
-                            S16[(2 * j) * 256 + tid] = make_int4(re[4 * j].f, im[4 * j].f, re[4 * j + 1].f, im[4 * j + 1].f);
-                            S16[(2 * j + 1) * 256 + tid] = make_int4(re[4 * j + 2].f, im[4 * j + 2].f, re[4 * j + 3].f, im[4 * j + 3].f);
+                            v = ownS[4 + j];
+                            ownS[2 * j] = make_int4(re[4 * j].f, im[4 * j].f, re[4 * j + 1].f, im[4 * j + 1].f);
+                            ownS[2 * j + 1] = make_int4(re[4 * j + 2].f, im[4 * j + 2].f, re[4 * j + 3].f, im[4 * j + 3].f);
                         }
                         const int x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
                         }
                     }
                 }
-                if (h == 0) prefetch(S16 + tid, 256, g0 + 4096);
+                if (h == 0) prefetch(S, g0 + 4096);         // every lane left the previous frame's STAGE 12 before the __syncwarp above
                 round32<4, DIT, MODE, KLO>(re, im, p, 0, TwRegs32{lwr, lwi}, true, false);
                 __syncwarp();
 #pragma unroll
@@ -168,13 +178,13 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
                 for (int m = 0; m < 16; ++m) { const int2 v = Q[pC + 288u * m]; re[m] = mk(v.x); im[m] = mk(v.y); }
                 __syncthreads();                           // the tile may be rewritten once every thread has read it
                 // the tile is idle until the next frame's A -> B change: land that frame's lower half in it
-                if (h == 1 && tile + gridDim.x < p.n_tiles) prefetch(P16 + lane, 32, (tile + gridDim.x) << 13);
+                if (h == 1 && tile + gridDim.x < p.n_tiles) prefetch(P, (tile + gridDim.x) << 13);
                 round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
             }
             // ---- STAGE 12 between the parked lower half and the registers; coalesced stores ----
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int4 a = S16[j * 256 + tid];
+                const int4 a = ownS[j];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int m = 2 * j + e;
