@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
     constexpr bool TMA_IN = !DIT;                  // DIF: first round reads stride-256 words -> stage via TMA
     // DIF, 4-stage last round: results go back into the thread's own tile slots and leave warp-coalesced
     // (stored directly, a warp instruction would write 32 separate 16-byte pieces at a 64-byte pitch)
-    constexpr bool COALESCE = !DIT && !NAT && R0 == 4 && NR == 3;
+    constexpr bool COALESCE = !DIT && !NAT && R0 == 4;
     // DIT, 4-stage first round: a thread needs its own 16 contiguous samples (64 bytes).  Loaded directly, a
     // warp instruction would touch 32 separate 16-byte pieces at a 64-byte pitch, so the WARP fetches its
     // 2 KB as 512 contiguous bytes per cp.async instruction into a skewed landing tile, one tile ahead.
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const unsigned i = w0 + 4u * lane + 128u * c;
-                    *reinterpret_cast<uint4 *>(p.out + g0 + i) = *reinterpret_cast<const uint4 *>(sm + phys(i));
+                    if (full || g0 + i < p.total) *reinterpret_cast<uint4 *>(p.out + g0 + i) = *reinterpret_cast<const uint4 *>(sm + phys(i));
                 }
             } else if (NAT) {
                 __syncthreads();

@@ -44,7 +44,7 @@ struct Fast32Params {
 __host__ __device__ constexpr unsigned phys8(unsigned i) { return i + 2u * (i >> 4); }
 constexpr unsigned kTile8 = 4608;
 constexpr unsigned kHead32 = 128 + 15 * 16 * 8;
-constexpr unsigned kStage32 = 16 * 256 * 8;   // prefetch staging: 16 slots x 256 threads x 8 bytes
+constexpr unsigned kStage32 = 256 * 9 * 16;   // prefetch staging: 16 slots x 256 threads x 8 bytes, or 256 x (8 + 1 pad) x 16 bytes
 
 // one scalar of a sample: the value and (TRUNCATE only; dead code elsewhere) its floor-half, which is
 // all a TRUNCATE butterfly ever reads (inputs sliced (DTW-1 downto 1), int_dif2_fly.vhd:150-153)
@@ -306,18 +306,32 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
     constexpr int LOF = RF == 0 ? 0 : R0 + 4 * (RF - 1);
     constexpr int RRF = RF == 0 ? R0 : 4;
     const unsigned basef = (tid & ((1u << LOF) - 1u)) | ((tid >> LOF) << (LOF + RRF));
-    // DIT with a 4-stage first round reads 16 contiguous samples per thread: those travel as 16-byte pieces
-    // into slots [piece][tid] (8 pieces of two samples, or 4 pieces of four packed 16-bit samples)
+    // DIT with a 4-stage first round reads 16 contiguous samples per thread.  The WARP fetches its 512 samples as
+    // 512 contiguous bytes per cp.async instruction (a thread copying its own 128 bytes would touch 32 lines per
+    // instruction); piece k lands in slot [owner thread][k mod pieces-per-thread] of a thread-major table whose
+    // 9-slot pitch keeps the owner's LDS.128 conflict-free
     constexpr bool PIECES = DIT && R0 == 4;
+    const unsigned lane = tid & 31u, wbase = tid & ~31u;
     auto prefetch = [&](long long t) {
         const char *src = reinterpret_cast<const char *>(p.in) + ((t << 12) + basef) * esz;
         if (PIECES) {
+            const char *wsrc = reinterpret_cast<const char *>(p.in) + ((t << 12) + (wbase << 4)) * esz + 16u * lane;
+            int4 *st16 = reinterpret_cast<int4 *>(stage);
+            if (p.in_sb == 4) {                            // piece k = lane + 32 j: owner k >> 3, slot k & 7
+                int4 *d = st16 + (wbase + (lane >> 3)) * 9 + (lane & 7u);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < esz) {
-                    const unsigned d = (unsigned)__cvta_generic_to_shared(stage + (j * 256 + tid) * 16);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 16 * j) : "memory");
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned a = (unsigned)__cvta_generic_to_shared(d + 36 * j);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(wsrc + 512 * j) : "memory");
                 }
+            } else {                                       // four packed samples per piece: owner k >> 2, slot k & 3
+                int4 *d = st16 + (wbase + (lane >> 2)) * 9 + (lane & 3u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned a = (unsigned)__cvta_generic_to_shared(d + 72 * j);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(wsrc + 512 * j) : "memory");
+                }
+            }
         } else {
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
@@ -376,18 +390,19 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
             if (first && staged) {                    // this tile was prefetched into the thread's slots
                 cp_async_wait_all();
                 if (PIECES) {
-                    const int4 *st16 = reinterpret_cast<const int4 *>(stage);
+                    __syncwarp();                          // the other lanes' pieces of this warp's block have landed too
+                    const int4 *st16 = reinterpret_cast<const int4 *>(stage) + tid * 9;
                     int a[16], b[16];
                     if (p.in_sb == 4) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const int4 v = st16[j * 256 + tid];
+                            const int4 v = st16[j];
                             a[2 * j] = v.x; b[2 * j] = v.y; a[2 * j + 1] = v.z; b[2 * j + 1] = v.w;
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int4 v = st16[j * 256 + tid];
+                            const int4 v = st16[j];
                             const int x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) { a[4 * j + e] = (int)(short)(x[e] & 0xffff); b[4 * j + e] = x[e] >> 16; }
@@ -411,6 +426,7 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
                 }
                 const long long nt = tile + gridDim.x;    // refill the slots with this CTA's next tile
                 staged = nt < p.n_tiles && ((nt + 1) << 12) <= p.total;
+                if (PIECES) __syncwarp();                 // every lane has drained its slots of the warp's block
                 if (staged) prefetch(nt);
             } else {
 #pragma unroll
