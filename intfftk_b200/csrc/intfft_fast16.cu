@@ -241,12 +241,11 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
     constexpr bool TMA_IN = !DIT;                  // DIF: first round reads stride-256 words -> stage via TMA
     // DIF, 4-stage last round: results go back into the thread's own tile slots and leave warp-coalesced
     // (stored directly, a warp instruction would write 32 separate 16-byte pieces at a 64-byte pitch)
-    constexpr bool COALESCE = !DIT && !NAT && R0 == 4;
+    constexpr bool COALESCE = !DIT && !NAT;
     // DIT, 4-stage first round: a thread needs its own 16 contiguous samples (64 bytes).  Loaded directly, a
     // warp instruction would touch 32 separate 16-byte pieces at a 64-byte pitch, so the WARP fetches its
     // 2 KB as 512 contiguous bytes per cp.async instruction into a skewed landing tile, one tile ahead.
-    constexpr bool CP_IN = DIT && R0 == 4;
-
+    constexpr bool CP_IN = DIT;
     static_assert(!MIDSM || (NR == 3 && R0 == 4), "MIDSM is for the three-round 4+4+4 schedule");
     // dynamic shared memory: [bar 2 x u64 | pad to 128] [mid twiddles 15 x 16 x int2] [work 2 x kTileWords]
     //                        [stage 2 x 4096 (DIF only)]
@@ -260,6 +259,13 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
     const unsigned tid = threadIdx.x;
     const int sh_full = p.sh_full, sh_half = p.sh_half;
     const bool tid_odd = tid & 1u;
+    // In the lowest round a warp owns 16 >> R0 runs of 32 << R0 contiguous samples (a thread: 1 << R0 contiguous
+    // samples per run).  16-byte piece q = lane + 32 c of the warp's 128 -> first sample inside the tile:
+    auto warp_piece = [&](int c) {
+        const unsigned q = (tid & 31u) + 32u * c;
+        return ((tid & ~31u) << R0) + ((q >> (3 + R0)) << (8 + R0)) + 4u * (q & ((8u << R0) - 1u));
+    };
+
 
     if (TMA_IN) {
         if (tid == 0) {
@@ -278,13 +284,12 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
     }
 
     auto prefetch_warp = [&](long long tile) {
-        const unsigned w0 = (tid & ~31u) << 4, lane = tid & 31u;
-        const long long g = (tile << 12) + w0;
+        const long long g = tile << 12;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const unsigned i = 4u * lane + 128u * j;               // sample offset inside the warp's 512
+            const unsigned i = warp_piece(j);
             const bool in_range = g + i < p.total;                  // p.total is a multiple of 4 samples
-            cp_async_16z(land + phys(w0 + i), in_range ? p.in + g + i : p.in, in_range ? 16u : 0u);
+            cp_async_16z(land + phys(i), in_range ? p.in + g + i : p.in, in_range ? 16u : 0u);
         }
         cp_async_commit_group();
     };
@@ -371,14 +376,19 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                     if (tile + gridDim.x < p.n_tiles) prefetch_warp(tile + gridDim.x);
                 }
             } else {
+                if (first && CP_IN) { cp_async_wait_group0(); __syncwarp(); }
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
                     const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
                     uint32_t x;
                     if (first && TMA_IN) x = stage[it & 1][base + off];
-                    else if (first) x = (full || (g0 + base + off) < p.total) ? __ldg(p.in + g0 + base + off) : 0u;
+                    else if (first) x = land[pbase + phys(off)];          // DIT: landed by the warp (zero-filled past the end)
                     else x = sm[pbase + phys(off)];
                     unpack<DW16>(x, p.dw, re[m], im[m]);
+                }
+                if (first && CP_IN) {
+                    __syncwarp();
+                    if (tile + gridDim.x < p.n_tiles) prefetch_warp(tile + gridDim.x);
                 }
             }
 
@@ -421,8 +431,8 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                     const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
                     const uint32_t x = (RAW && r > 0 && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632)
                                                                  : pack(re[m], im[m]);
-                    if (last) { if (full || (g0 + base + off) < p.total) p.out[g0 + base + off] = x; }
-                    else sm[pbase + phys(off)] = x;
+                    if (last && !COALESCE) { if (full || (g0 + base + off) < p.total) p.out[g0 + base + off] = x; }
+                    else sm[pbase + phys(off)] = x;                       // last round: in place, stored below
                 }
             }
             // The hand-over between the two LOWEST rounds of the 4+4+4 schedule stays inside a warp
@@ -434,12 +444,11 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                 else __syncthreads();
                 if (NAT && rr == 0) prefetch_next();
             } else if (COALESCE) {
-                // a warp owns 512 contiguous samples after the warp-local hand-over: 512 contiguous bytes per store
+                // the warp's own runs of the tile, 512 contiguous bytes per store (up to the run length)
                 __syncwarp();
-                const unsigned w0 = (tid & ~31u) << 4, lane = tid & 31u;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const unsigned i = w0 + 4u * lane + 128u * c;
+                    const unsigned i = warp_piece(c);
                     if (full || g0 + i < p.total) *reinterpret_cast<uint4 *>(p.out + g0 + i) = *reinterpret_cast<const uint4 *>(sm + phys(i));
                 }
             } else if (NAT) {
