@@ -306,23 +306,30 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
     constexpr int LOF = RF == 0 ? 0 : R0 + 4 * (RF - 1);
     constexpr int RRF = RF == 0 ? R0 : 4;
     const unsigned basef = (tid & ((1u << LOF) - 1u)) | ((tid >> LOF) << (LOF + RRF));
-    // DIT with a 4-stage first round reads 16 contiguous samples per thread.  The WARP fetches its 512 samples as
-    // 512 contiguous bytes per cp.async instruction (a thread copying its own 128 bytes would touch 32 lines per
-    // instruction); piece k lands in slot [owner thread][k mod pieces-per-thread] of a thread-major table whose
-    // 9-slot pitch keeps the owner's LDS.128 conflict-free
-    constexpr bool PIECES = DIT && R0 == 4;
+    // In the lowest round a warp owns 16 >> R0 runs of 32 << R0 contiguous samples (a thread: 1 << R0 contiguous
+    // samples of each run).  Read or written per thread, a warp instruction would touch up to 32 lines, so both the
+    // DIT input and the DIF output move per WARP: 16-byte piece q = lane + 32 j of the warp's 256 pieces (two
+    // int32 samples each) is at tile-local sample warp_piece(j), 512 contiguous bytes per instruction.
     const unsigned lane = tid & 31u, wbase = tid & ~31u;
+    auto warp_piece = [&](int j) {
+        const unsigned q = lane + 32u * j;
+        return (wbase << R0) + ((q >> (4 + R0)) << (8 + R0)) + 2u * (q & ((16u << R0) - 1u));
+    };
+    // DIT input lands (cp.async, one tile ahead) in a tile-skewed copy of the block (32-bit containers, every R0),
+    // or, for packed 16-bit input with a 4-stage first round, in a thread-major table with a 9-slot pitch
+    const bool pieces = DIT && (R0 == 4 || p.in_sb == 4);
+    int2 *land = reinterpret_cast<int2 *>(stage);
     auto prefetch = [&](long long t) {
         const char *src = reinterpret_cast<const char *>(p.in) + ((t << 12) + basef) * esz;
-        if (PIECES) {
+        if (pieces) {
             const char *wsrc = reinterpret_cast<const char *>(p.in) + ((t << 12) + (wbase << 4)) * esz + 16u * lane;
             int4 *st16 = reinterpret_cast<int4 *>(stage);
-            if (p.in_sb == 4) {                            // piece k = lane + 32 j: owner k >> 3, slot k & 7
-                int4 *d = st16 + (wbase + (lane >> 3)) * 9 + (lane & 7u);
+            if (p.in_sb == 4) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const unsigned a = (unsigned)__cvta_generic_to_shared(d + 36 * j);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(wsrc + 512 * j) : "memory");
+                    const unsigned i = warp_piece(j);
+                    const unsigned a = (unsigned)__cvta_generic_to_shared(land + phys8(i));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(reinterpret_cast<const int2 *>(p.in) + (t << 12) + i) : "memory");
                 }
             } else {                                       // four packed samples per piece: owner k >> 2, slot k & 3
                 int4 *d = st16 + (wbase + (lane >> 2)) * 9 + (lane & 3u);
@@ -389,15 +396,23 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
 
             if (first && staged) {                    // this tile was prefetched into the thread's slots
                 cp_async_wait_all();
-                if (PIECES) {
+                if (pieces) {
                     __syncwarp();                          // the other lanes' pieces of this warp's block have landed too
                     const int4 *st16 = reinterpret_cast<const int4 *>(stage) + tid * 9;
                     int a[16], b[16];
-                    if (p.in_sb == 4) {
+                    if (p.in_sb == 4 && R0 == 4) {
+                        const int4 *own = reinterpret_cast<const int4 *>(land + pbase);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const int4 v = st16[j];
+                            const int4 v = own[j];
                             a[2 * j] = v.x; b[2 * j] = v.y; a[2 * j + 1] = v.z; b[2 * j + 1] = v.w;
+                        }
+                    } else if (p.in_sb == 4) {
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) {
+                            const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
+                            const int2 v = land[pbase + phys8(off)];
+                            a[m] = v.x; b[m] = v.y;
                         }
                     } else {
 #pragma unroll
@@ -426,7 +441,7 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
                 }
                 const long long nt = tile + gridDim.x;    // refill the slots with this CTA's next tile
                 staged = nt < p.n_tiles && ((nt + 1) << 12) <= p.total;
-                if (PIECES) __syncwarp();                 // every lane has drained its slots of the warp's block
+                if (pieces) __syncwarp();                 // every lane has drained its slots of the warp's block
                 if (staged) prefetch(nt);
             } else {
 #pragma unroll
@@ -452,20 +467,19 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
             else if (r == 1) round32<4, DIT, MODE, KIND>(re, im, p, R0, TwSmem32{midtw + (tid & ((1u << R0) - 1u)), 1 << R0}, false, tid_odd);
             else round32<4, DIT, MODE, KIND>(re, im, p, R0 + 4, TwRegs32{uwr, uwi}, false, tid_odd);
 
-            if (last && full && !DIT && R0 == 4 && p.out_sb == 4) {
-                // DIF ends with 16 contiguous samples (128 bytes) per thread; stored directly, one instruction
-                // would touch 32 lines.  The thread's own tile slots take the results in place (the
-                // preceding hand-over was warp-local, so the warp owns these 512 samples), then the warp
-                // writes 512 contiguous bytes per instruction.
+            if (last && full && !DIT && p.out_sb == 4) {
+                // DIF results go back into the thread's own tile slots (the ones it read for this round) and
+                // leave per warp, 512 contiguous bytes per instruction (up to the run length)
 #pragma unroll
-                for (int m = 0; m < 16; ++m) sm[pbase + m] = make_int2(re[m].f, im[m].f);
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
+                    sm[pbase + phys8(off)] = make_int2(re[m].f, im[m].f);
+                }
                 __syncwarp();
-                const unsigned w0 = (tid & ~31u) << 4, lane = tid & 31u;
-                int4 *dst = reinterpret_cast<int4 *>(reinterpret_cast<int2 *>(p.out) + g0 + w0);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const unsigned i = w0 + 2u * lane + 64u * j;
-                    dst[lane + 32 * j] = *reinterpret_cast<const int4 *>(sm + phys8(i));
+                    const unsigned i = warp_piece(j);
+                    *reinterpret_cast<int4 *>(reinterpret_cast<int2 *>(p.out) + g0 + i) = *reinterpret_cast<const int4 *>(sm + phys8(i));
                 }
             } else if (last && full) {
 #pragma unroll

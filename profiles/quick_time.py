@@ -83,6 +83,13 @@ def f12():
     print(f"exec_natural c5: {timeit(lambda: core.exec_natural(x, y), 5)*1e3:8.1f} us   (exec alone {timeit(lambda: core.exec(x, y), 5)*1e3:8.1f} us)", flush=True)
     core.close()
 
+def small32():
+    for d in (0, 1):
+        for n in (9, 10, 11):
+            time_plan(65536 << (12 - n), steps=5, direction=d, NFFT=n, DATA_WIDTH=18, FORMAT=0)
+        for n in (14, 15):
+            time_plan(65536 >> (n - 12), steps=5, direction=d, NFFT=n, DATA_WIDTH=18, FORMAT=0)
+
 def c3():
     time_plan(4096, steps=10, NFFT=16, DATA_WIDTH=24, FORMAT=1)
 
