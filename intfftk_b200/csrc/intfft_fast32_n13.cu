@@ -3,7 +3,7 @@
 // read from HBM once and written once (16 B instead of 32 B per sample at c5), and one of the two
 // load / store / address-generation sequences disappears.
 //
-// Shape: a CTA of 256 threads (two per SM, so one CTA's exchanges overlap the other's arithmetic) owns an
+// Shape: a CTA of 256 threads (three per SM, so one CTA's exchanges overlap the others' arithmetic) owns an
 // 8192-sample frame and walks its two 4096-sample halves one after the other.  A thread keeps 16 samples
 // in registers; per half, STAGE 0..11 run as three register rounds
 //     A: STAGE 0..3  (16 contiguous samples)        twiddles: kernel parameters (constant bank)
