@@ -150,8 +150,9 @@ template <int MODE> __device__ __forceinline__ void addsub32(const V &a, const V
         yf = msub2(b.h, xf);
     } else if (MODE == MODE_ROUND) {            // (v >> 1) + v(0) == (v + 1) >> 1
         xf = (int)((unsigned)a.f + (unsigned)b.f + 1u) >> 1;
-        // the rounded difference can reach 2^(ow-1) and is kept in ow bits by the reference
-        yf = sx((int)((unsigned)a.f - (unsigned)b.f + 1u) >> 1, ow);
+        // (a - b + 1) >> 1 == ((a + b + 1) >> 1) - b exactly (ROUNDING plans keep a spare bit, so the sum cannot
+        // overflow the lane); the rounded difference can reach 2^(ow-1) and is kept in ow bits by the reference
+        yf = sx((int)((unsigned)xf - (unsigned)b.f), ow);
     } else {
         xf = (int)((unsigned)a.f + (unsigned)b.f);
         yf = (int)((unsigned)a.f - (unsigned)b.f);
