@@ -397,6 +397,27 @@ def test_bitrev_order_unaligned_buffers_take_the_scalar_path(ib, oracle):
     assert np.array_equal(got, oracle.bitrev(nfft, x))
 
 
+def test_full_c2_batch_checksum_matches_oracle(ib, oracle):
+    """The WHOLE BASELINE c2 batch (65536 frames x 4096 points): device stimulus -> device FFT -> device checksum
+    against the same stimulus pushed through the multithreaded C oracle on the host."""
+    nfft, batch, seed = 12, 65536, 0x696E7466
+    g = ib.Generics(NFFT=nfft, DATA_WIDTH=16, FORMAT=0)
+    core = ib.Core(g, batch, 0)
+    x = core.new_input()
+    ib.fill_random(x, 16, seed)
+    y = core.exec(x)
+    got = ib.checksum(y)
+    hx = oracle.fill_random(batch * (1 << nfft) * 2, 16, seed).reshape(batch, 1 << nfft, 2)
+    assert oracle.checksum(hx) == ib.checksum(x)
+    want = oracle.batch(oracle.generics(nfft), hx)
+    assert oracle.checksum(want) == got
+    # and the natural-order wrapper on the same batch: a permutation of every frame
+    z = core.exec_natural(x)
+    for f in (0, 777, 65535):
+        assert np.array_equal(z[f].cpu().numpy()[None], oracle.bitrev(nfft, want[f][None]))
+    core.close()
+
+
 def test_fft_ifft_pair_roundtrip_full_c2_batch(ib, oracle):
     """Size-independent property at the full c2 size (65536 x 4096): FFT then IFFT returns x / N
     within the truncation bias; plus a checksum-of-frames comparison with the oracle on a sample."""
