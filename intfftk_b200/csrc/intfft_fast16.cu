@@ -84,6 +84,9 @@ __device__ __forceinline__ void cp_async_16z(void *smem_dst, const void *gsrc, u
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_group0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Only a pass's first round can meet values outside DATA_WIDTH (conv_std_logic_vector wrap of the stimulus):
+// everything a later round reads from the exchange tile was produced here, already wrapped to DATA_WIDTH
+// bits and sign-extended to 16, so those rounds take the cheap 16-bit unpack whatever DATA_WIDTH is.
 template <bool DW16>
 __device__ __forceinline__ void unpack(uint32_t x, int dw, int &re, int &im)
 {
@@ -373,10 +376,17 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                     } else {
                         v = *reinterpret_cast<const uint4 *>(sm + pbase + phys(4 * c));
                     }
-                    unpack<DW16>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
-                    unpack<DW16>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
-                    unpack<DW16>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
-                    unpack<DW16>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                    if (first) {
+                        unpack<DW16>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
+                        unpack<DW16>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
+                        unpack<DW16>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
+                        unpack<DW16>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                    } else {
+                        unpack<true>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
+                        unpack<true>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
+                        unpack<true>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
+                        unpack<true>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                    }
                 }
                 if (first && CP_IN) {                             // every lane has drained the warp's region
                     __syncwarp();
@@ -391,7 +401,8 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                     if (first && TMA_IN) x = stage[it & 1][base + off];
                     else if (first) x = land[pbase + phys(off)];          // DIT: landed by the warp (zero-filled past the end)
                     else x = sm[pbase + phys(off)];
-                    unpack<DW16>(x, p.dw, re[m], im[m]);
+                    if (first) unpack<DW16>(x, p.dw, re[m], im[m]);
+                    else unpack<true>(x, p.dw, re[m], im[m]);
                 }
                 if (first && CP_IN) {
                     __syncwarp();
@@ -587,7 +598,8 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
                     const uint32_t x = (first ? st : work)[pbase + phys((unsigned)m << lo)];
-                    unpack<DW16>(x, p.dw, re[m], im[m]);
+                    if (first) unpack<DW16>(x, p.dw, re[m], im[m]);
+                    else unpack<true>(x, p.dw, re[m], im[m]);
                 }
                 constexpr bool RAW = !DIT && DW16;
                 if (lo == 8) round_regs<8, 4, DIT, DW16, MODE, RAW && (NR == 2)>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);

@@ -482,6 +482,22 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
                     const unsigned i = warp_piece(j);
                     *reinterpret_cast<int4 *>(reinterpret_cast<int2 *>(p.out) + g0 + i) = *reinterpret_cast<const int4 *>(sm + phys8(i));
                 }
+            } else if (last && full && !DIT) {
+                // packed 16-bit output (16-bit data with TWDL_WIDTH > 16): the packed word takes the first half of
+                // the thread's own slot; the warp then gathers four of them per 16-byte store
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
+                    sm[pbase + phys8(off)].x = (int)__byte_perm((unsigned)re[m].f, (unsigned)im[m].f, 0x5410);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned q = lane + 32u * j;     // piece of four samples among the warp's 128
+                    const unsigned i = (wbase << R0) + ((q >> (3 + R0)) << (8 + R0)) + 4u * (q & ((8u << R0) - 1u));
+                    const int4 a = *reinterpret_cast<const int4 *>(sm + phys8(i)), b = *reinterpret_cast<const int4 *>(sm + phys8(i) + 2);
+                    *reinterpret_cast<int4 *>(reinterpret_cast<unsigned *>(p.out) + g0 + i) = make_int4(a.x, a.z, b.x, b.z);
+                }
             } else if (last && full) {
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {

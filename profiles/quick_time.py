@@ -90,6 +90,30 @@ def small32():
         for n in (14, 15):
             time_plan(65536 >> (n - 12), steps=5, direction=d, NFFT=n, DATA_WIDTH=18, FORMAT=0)
 
+def modes():
+    """every mode / width class at 4096 points (and a few two-pass sizes): looks for pathological paths"""
+    for dw in (8, 12, 14, 16, 18, 20, 24, 27, 31, 32, 36, 40):
+        for fmt, rnd in ((0, 0), (0, 1), (1, 0)):
+            for d in (0, 1):
+                if d == 0 and fmt == 1 and rnd == 1:
+                    continue
+                if dw + fmt * 12 > 64:
+                    continue
+                try:
+                    time_plan(16384, steps=3, direction=d, NFFT=12, DATA_WIDTH=dw, FORMAT=fmt, RNDMODE=rnd)
+                except Exception as e:
+                    print("skip", dw, fmt, rnd, d, e, flush=True)
+    for tw in (10, 18, 24):
+        for d in (0, 1):
+            time_plan(16384, steps=3, direction=d, NFFT=12, DATA_WIDTH=16, TWDL_WIDTH=tw, FORMAT=0)
+
+def modes_mini():
+    for d in (0, 1):
+        time_plan(16384, steps=3, direction=d, NFFT=12, DATA_WIDTH=12, FORMAT=0)
+        time_plan(16384, steps=3, direction=d, NFFT=12, DATA_WIDTH=12, FORMAT=0, RNDMODE=1)
+        time_plan(16384, steps=3, direction=d, NFFT=12, DATA_WIDTH=16, TWDL_WIDTH=18, FORMAT=0)
+        time_plan(256, steps=3, direction=d, NFFT=18, DATA_WIDTH=14, FORMAT=0)
+
 def c3():
     time_plan(4096, steps=10, NFFT=16, DATA_WIDTH=24, FORMAT=1)
 
