@@ -46,6 +46,7 @@ __host__ __device__ constexpr unsigned phys64(unsigned i) { return i + (i >> 4);
 
 struct Stg64 {
     int s, ow, dtwc;
+    int k, sp;               // KIND 3: pre-shift of each product / post-shift of their sum for THIS stage
 };
 template <bool DIT, int MODE> __device__ __forceinline__ Stg64 stage64(const Fast64Params &p, int s)
 {
@@ -56,6 +57,10 @@ template <bool DIT, int MODE> __device__ __forceinline__ Stg64 stage64(const Fas
     const int dtw = p.dw + ii * FORMAT;
     st.ow = dtw + FORMAT;
     st.dtwc = DIT ? dtw : st.ow;
+    // the single arrangement is the double one without pre-shift (intfft_fast32.cuh: stage_of)
+    const bool dbl = st.dtwc >= p.cm.lim_single;
+    st.k = dbl ? p.cm.k_pre : 0;
+    st.sp = dbl ? p.cm.sh_post : p.cm.sh_single;
     return st;
 }
 
@@ -117,13 +122,32 @@ __device__ __forceinline__ int64_t field64(int64_t t, int sh, int w)
     return mk64(__funnelshift_r(lo32(t), (unsigned)hi32(t), sh), (int)((unsigned)hi32(t) << (64 - sh - w)) >> (64 - w));
 }
 
-// KIND: 0 single, 1 double, 2 triple (the same for every multiplying stage of the pass)
+// keep the low w bits of v, sign-extended, for ANY 2 <= w <= 64 (grid-uniform w, branch-free): the low word is
+// sign-extended from min(w, 32) bits, the high word from w - 32 bits or taken from the low word's sign
+__device__ __forceinline__ int64_t wrap_any(int64_t v, int w)
+{
+    const int s1 = w >= 32 ? 0 : 32 - w, s2 = w > 32 ? 64 - w : 0;
+    const int lo = (int)(lo32(v) << s1) >> s1;
+    const int hi_w = (int)((unsigned)hi32(v) << s2) >> s2;
+    return mk64((unsigned)lo, w > 32 ? hi_w : (lo >> 31));
+}
+// bits [sh + w - 1 : sh] of t, sign-extended, 0 <= sh < 32, any w with sh + w <= 64
+__device__ __forceinline__ int64_t field_any(int64_t t, int sh, int w) { return wrap_any(sra64(t, sh), w); }
+
+// KIND: 0 single, 1 double, 2 triple (the same for every multiplying stage of the pass, every width beyond 32
+// bits); 3 = single / double chosen per stage, any width (plans whose STAGE 7..0 cross the 32-bit line)
 template <int KIND>
-__device__ __forceinline__ void cmul64(int64_t dr, int64_t di, int wr, int wi, const CmultConsts &cm, int dtwc,
+__device__ __forceinline__ void cmul64(int64_t dr, int64_t di, int wr, int wi, const CmultConsts &cm, const Stg64 &st,
                                        int64_t &o_re, int64_t &o_im)
 {
+    const int dtwc = st.dtwc;
     const Split r = split64(dr), i = split64(di);
-    if (KIND == 0) {
+    if (KIND == 3) {
+        const int64_t tr = sra64(mul64x32(r, wr), st.k) - sra64(mul64x32(i, wi), st.k);
+        const int64_t ti = sra64(mul64x32(r, wi), st.k) + sra64(mul64x32(i, wr), st.k);
+        o_re = field_any(tr, st.sp, dtwc);
+        o_im = field_any(ti, st.sp, dtwc);
+    } else if (KIND == 0) {
         const int64_t tr = mad64x32(i, -wi, mul64x32(r, wr));
         const int64_t ti = mad64x32(i, wr, mul64x32(r, wi));
         o_re = field64(tr, cm.sh_single, dtwc);
@@ -145,7 +169,7 @@ __device__ __forceinline__ void cmul64(int64_t dr, int64_t di, int wr, int wi, c
 __device__ __forceinline__ int64_t negq64(int64_t v) { return (v >> 63) - v; }
 
 // `ow` > 32: only the ROUNDING difference can leave it (see addsub<> in intfft_arith.cuh)
-template <int MODE> __device__ __forceinline__ void addsub64(int64_t a, int64_t b, int ow, int64_t &ad, int64_t &su)
+template <int MODE, bool ANYW = false> __device__ __forceinline__ void addsub64(int64_t a, int64_t b, int ow, int64_t &ad, int64_t &su)
 {
     if (MODE == MODE_TRUNC) {
         const int64_t ha = sra64(a, 1), hb = sra64(b, 1);
@@ -154,7 +178,7 @@ template <int MODE> __device__ __forceinline__ void addsub64(int64_t a, int64_t 
     } else if (MODE == MODE_ROUND) {
         const int64_t s = (int64_t)((uint64_t)a + (uint64_t)b + 1u), d = (int64_t)((uint64_t)a - (uint64_t)b + 1u);
         ad = sra64(s, 1);
-        su = wrap_hi(sra64(d, 1), ow);
+        su = ANYW ? wrap_any(sra64(d, 1), ow) : wrap_hi(sra64(d, 1), ow);
     } else {
         ad = (int64_t)((uint64_t)a + (uint64_t)b);
         su = (int64_t)((uint64_t)a - (uint64_t)b);
@@ -168,8 +192,8 @@ __device__ __forceinline__ void fly64(const Stg64 &st, bool odd, const CmultCons
     using T = int64_t;
     if (!DIT) {
         T xr, xi, sr, si;
-        addsub64<MODE>(ar, br, st.ow, xr, sr);
-        addsub64<MODE>(ai, bi, st.ow, xi, si);
+        addsub64<MODE, KIND == 3>(ar, br, st.ow, xr, sr);
+        addsub64<MODE, KIND == 3>(ai, bi, st.ow, xi, si);
         ar = xr;
         ai = xi;
         if (st.s == 0) {
@@ -179,7 +203,7 @@ __device__ __forceinline__ void fly64(const Stg64 &st, bool odd, const CmultCons
             br = odd ? si : sr;
             bi = odd ? negq64(sr) : si;
         } else {
-            cmul64<KIND>(sr, si, wr, wi, cm, st.dtwc, br, bi);
+            cmul64<KIND>(sr, si, wr, wi, cm, st, br, bi);
         }
     } else {
         T wr_, wi_;
@@ -191,13 +215,13 @@ __device__ __forceinline__ void fly64(const Stg64 &st, bool odd, const CmultCons
             wi_ = odd ? br : bi;
         } else {                                      // multiplier fed with swapped re / im, outputs swapped back
             T o_re, o_im;
-            cmul64<KIND>(bi, br, wr, wi, cm, st.dtwc, o_re, o_im);
+            cmul64<KIND>(bi, br, wr, wi, cm, st, o_re, o_im);
             wi_ = o_re;
             wr_ = o_im;
         }
         T xr, xi, yr, yi;
-        addsub64<MODE>(ar, wr_, st.ow, xr, yr);
-        addsub64<MODE>(ai, wi_, st.ow, xi, yi);
+        addsub64<MODE, KIND == 3>(ar, wr_, st.ow, xr, yr);
+        addsub64<MODE, KIND == 3>(ai, wi_, st.ow, xi, yi);
         ar = xr; ai = xi;
         br = yr; bi = yi;
     }
@@ -329,9 +353,10 @@ __global__ void __launch_bounds__(256, 2) fast64_kernel(const __grid_constant__ 
 template <bool DIT, int MODE> cudaError_t launch_k(const Fast64Params &p, int kind, int grid, cudaStream_t st)
 {
     using K = void (*)(const Fast64Params);
-    // KIND 0 (single DSP48 pair) needs dtwc < 28 and so never meets this kernel's "wraps above 32 bits" rule
-    if (kind != 1 && kind != 2) return cudaErrorInvalidValue;
-    K k = kind == 1 ? (K)fast64_kernel<DIT, MODE, 1> : (K)fast64_kernel<DIT, MODE, 2>;
+    // KIND 0 (single DSP48 pair) needs dtwc < 28 and so never meets the "every width beyond 32 bits" rule of the
+    // specialised instances; plans with such stages run the per-stage instance (3)
+    if (kind < 1 || kind > 3) return cudaErrorInvalidValue;
+    K k = kind == 1 ? (K)fast64_kernel<DIT, MODE, 1> : (kind == 2 ? (K)fast64_kernel<DIT, MODE, 2> : (K)fast64_kernel<DIT, MODE, 3>);
     const int smem = 8 * kWarpSlots * 16;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -341,22 +366,27 @@ template <bool DIT, int MODE> cudaError_t launch_k(const Fast64Params &p, int ki
 
 }  // namespace
 
-// multiplier arrangement shared by every multiplying stage (STAGE 2..7) of the pass; -1 when they differ
-// or when some stage of the pass still wraps at <= 32 bits (the kernel's slices assume a live high word)
+// Which instance runs STAGE 7..0 of this plan: 1 / 2 when every stage of the pass is wider than 32 bits and all
+// multiplying stages (STAGE 2..7) share the double / triple arrangement; 3 (per-stage single / double, any
+// width) when some stage still wraps at <= 32 bits or the arrangements differ; -1 when a triple stage is mixed
+// with others (left to the generic kernel).
 int fast64_uniform_kind(const PassParams &kp, bool dit)
 {
     int kind = -1;
+    bool all_wide = true, uniform = true, any_triple = false;
     for (int s = 0; s < 8; ++s) {
         const int ii = dit ? s : kp.n - 1 - s;
         const int dtw = kp.dw + ii * kp.format;
         const int dtwc = dit ? dtw : dtw + kp.format;
-        if (dtwc <= 32 || dtw + kp.format <= 32) return -1;
+        if (dtwc <= 32 || dtw + kp.format <= 32) all_wide = false;
         if (s < 2) continue;
         const int k = dtwc < kp.cm.lim_single ? 0 : (dtwc < kp.cm.lim_dbl ? 1 : 2);
-        if (kind >= 0 && k != kind) return -1;
+        if (k == 2) any_triple = true;
+        if (kind >= 0 && k != kind) uniform = false;
         kind = k;
     }
-    return kind;
+    if (all_wide && uniform && kind >= 1) return kind;
+    return any_triple ? -1 : 3;
 }
 
 int launch_fast64(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,

@@ -114,6 +114,13 @@ def modes_mini():
         time_plan(16384, steps=3, direction=d, NFFT=12, DATA_WIDTH=16, TWDL_WIDTH=18, FORMAT=0)
         time_plan(256, steps=3, direction=d, NFFT=18, DATA_WIDTH=14, FORMAT=0)
 
+def wide():
+    for d in (0, 1):
+        time_plan(16384, steps=3, direction=d, NFFT=12, DATA_WIDTH=24, FORMAT=1)
+        time_plan(1024, steps=3, direction=d, NFFT=16, DATA_WIDTH=18, FORMAT=1)
+        time_plan(16384, steps=3, direction=d, NFFT=12, DATA_WIDTH=32, FORMAT=0, RNDMODE=1)
+        time_plan(1024, steps=3, direction=d, NFFT=16, DATA_WIDTH=24, FORMAT=1)
+
 def c3():
     time_plan(4096, steps=10, NFFT=16, DATA_WIDTH=24, FORMAT=1)
 

@@ -167,7 +167,11 @@ LANE64 = [  # (nfft, dw, tw, xser, fmt, rnd): plans whose STAGE 7..0 run on the 
     (8, 36, 24, "NEW", 0, 1), (8, 38, 22, "OLD", 1, 0), (8, 40, 24, "NEW", 0, 0),                             # trpl52
     (12, 30, 16, "NEW", 1, 0), (12, 34, 16, "NEW", 1, 0), (12, 40, 16, "OLD", 0, 0), (13, 36, 16, "NEW", 0, 1),
     (14, 33, 17, "NEW", 0, 0), (15, 26, 16, "NEW", 1, 0), (16, 24, 16, "NEW", 1, 0), (16, 24, 16, "OLD", 1, 0),
-    (16, 38, 20, "NEW", 0, 0)]
+    (16, 38, 20, "NEW", 0, 0),
+    # STAGE 7..0 crossing the 32-bit line and / or mixing single and double arrangements: the per-stage instance
+    (12, 24, 16, "NEW", 1, 0), (12, 27, 16, "NEW", 1, 0), (12, 31, 16, "OLD", 1, 0), (8, 28, 16, "NEW", 1, 0),
+    (16, 18, 16, "NEW", 1, 0), (16, 20, 17, "OLD", 1, 0), (12, 32, 16, "NEW", 0, 1), (8, 30, 20, "NEW", 1, 0),
+    (12, 22, 18, "NEW", 1, 0), (8, 32, 16, "OLD", 0, 1), (12, 26, 24, "NEW", 1, 0)]
 
 
 @pytest.mark.parametrize("nfft,dw,tw,xser,fmt,rnd", LANE64)
