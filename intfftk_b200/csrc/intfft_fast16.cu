@@ -247,11 +247,12 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
     static_assert(!NAT || (NLOG2 == 12 && !DIT), "fused natural-order output: 4096-point DIF only");
     constexpr int R0 = ((NLOG2 - 1) % 4) + 1;      // stages in the lowest round
     constexpr int NR = 1 + (NLOG2 - R0) / 4;       // rounds; round r > 0 covers bits R0+4(r-1) .. +3
-    static_assert(NR >= 2 && NR <= 3, "supported: 2^5 .. 2^12 points");
+    static_assert(NR >= 1 && NR <= 3, "supported: 2^3 .. 2^12 points");
+    constexpr int NU = NR > 1 ? NR - 1 : 1;        // rounds above the lowest one (array extent, at least 1)
     constexpr bool TMA_IN = !DIT;                  // DIF: first round reads stride-256 words -> stage via TMA
     // DIF, 4-stage last round: results go back into the thread's own tile slots and leave warp-coalesced
     // (stored directly, a warp instruction would write 32 separate 16-byte pieces at a 64-byte pitch)
-    constexpr bool COALESCE = !DIT && !NAT;
+    constexpr bool COALESCE = (!DIT || NR == 1) && !NAT;   // (a one-round DIT ends in the lowest round as well)
     // DIT, 4-stage first round: a thread needs its own 16 contiguous samples (64 bytes).  Loaded directly, a
     // warp instruction would touch 32 separate 16-byte pieces at a 64-byte pitch, so the WARP fetches its
     // 2 KB as 512 contiguous bytes per cp.async instruction into a skewed landing tile, one tile ahead.
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
         }
         __syncthreads();
     }
-    int uwr[NR - 1][15], uwi[NR - 1][15];
+    int uwr[NU][15], uwi[NU][15];
 #pragma unroll
     for (int r = 1; r < NR; ++r) {
         if (MIDSM && r == 1) continue;
@@ -350,6 +351,9 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                 tma_load_1d(stage[(it + 1) & 1], p.in + (nt << 12), bytes, &bar[(it + 1) & 1]);
             }
         };
+        // 8- and 16-point frames run in ONE register round, so nothing else orders the tiles: every thread must
+        // have left the previous tile before its TMA landing buffer is refilled
+        if (NR == 1) __syncthreads();
         if (TMA_IN) {
             if (!NAT) prefetch_next();
             mbar_wait(&bar[it & 1], (it >> 1) & 1);
@@ -371,7 +375,9 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint4 v;
-                    if (first) {                                  // DIT: this thread's 64 bytes of the landed tile
+                    if (first && TMA_IN) {                        // 16-point DIF: straight from the (linear) TMA landing buffer
+                        v = *reinterpret_cast<const uint4 *>(stage[it & 1] + 16 * tid + 4 * c);
+                    } else if (first) {                           // DIT: this thread's 64 bytes of the landed tile
                         v = *reinterpret_cast<const uint4 *>(land + pbase + phys(4 * c));
                     } else {
                         v = *reinterpret_cast<const uint4 *>(sm + pbase + phys(4 * c));
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
             if (r == 0) round_regs<0, R0, DIT, DW16, MODE, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
             else if (r == 1 && MIDSM) round_regs<R0, 4, DIT, DW16, MODE, RAW>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
             else if (r == 1) round_regs<R0, 4, DIT, DW16, MODE, RAW>(re, im, TwRegs{uwr[0], uwi[0]}, tid_odd, sh_full, sh_half);
-            else round_regs<R0 + 4, 4, DIT, DW16, MODE, RAW>(re, im, TwRegs{uwr[NR - 2], uwi[NR - 2]}, tid_odd, sh_full, sh_half);
+            else round_regs<R0 + 4, 4, DIT, DW16, MODE, RAW>(re, im, TwRegs{uwr[NU - 1], uwi[NU - 1]}, tid_odd, sh_full, sh_half);
 
             // ---- hand the samples on: to the exchange tile, or to HBM after the last round ----
             if (r == 0 && R0 == 4) {
@@ -663,7 +669,7 @@ cudaError_t launch_n(const Fast16Params &p, int mode, bool dit, bool dw16, int g
 bool fast16_supported(const intfft_generics &g)
 {
     return g.format == 0 && g.use_fly == 1 && g.data_width <= 16 && g.twdl_width <= 16 &&
-           g.nfft_log2 >= 8 && g.nfft_log2 <= 20;
+           g.nfft_log2 >= 3 && g.nfft_log2 <= 20;
 }
 
 // top-bits pass of an NFFT >= 13 plan: kp.g in {4, 8}, kp.pb = NFFT - kp.g
@@ -725,6 +731,11 @@ int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const
     const bool dw16 = p.dw == 16;
     cudaError_t e;
     switch (pd.kp.g) {          // stage bits of this (contiguous) pass; == NFFT for single-pass plans
+    case 3: e = launch_n<3>(p, mode, dit, dw16, (int)grid, st); break;
+    case 4: e = launch_n<4>(p, mode, dit, dw16, (int)grid, st); break;
+    case 5: e = launch_n<5>(p, mode, dit, dw16, (int)grid, st); break;
+    case 6: e = launch_n<6>(p, mode, dit, dw16, (int)grid, st); break;
+    case 7: e = launch_n<7>(p, mode, dit, dw16, (int)grid, st); break;
     case 8: e = launch_n<8>(p, mode, dit, dw16, (int)grid, st); break;
     case 9: e = launch_n<9>(p, mode, dit, dw16, (int)grid, st); break;
     case 10: e = launch_n<10>(p, mode, dit, dw16, (int)grid, st); break;

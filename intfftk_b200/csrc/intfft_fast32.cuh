@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
 {
     constexpr int R0 = ((NLOG2 - 1) % 4) + 1;
     constexpr int NR = 1 + (NLOG2 - R0) / 4;
-    static_assert(NR >= 2 && NR <= 3, "supported: 2^5 .. 2^12 points per tile");
+    static_assert(NR >= 1 && NR <= 3, "supported: 2^3 .. 2^12 points per tile");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);                  // [15][1 << R0]
     int2(*work)[kTile8] = reinterpret_cast<int2(*)[kTile8]>(smem_raw + kHead32);
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
     };
     // DIT input lands (cp.async, one tile ahead) in a tile-skewed copy of the block (32-bit containers, every R0),
     // or, for packed 16-bit input with a 4-stage first round, in a thread-major table with a 9-slot pitch
-    const bool pieces = DIT && (R0 == 4 || p.in_sb == 4);
+    const bool pieces = (DIT || NR == 1) && (R0 == 4 || p.in_sb == 4);   // (a one-round DIF starts in the lowest round too)
     int2 *land = reinterpret_cast<int2 *>(stage);
     auto prefetch = [&](long long t) {
         const char *src = reinterpret_cast<const char *>(p.in) + ((t << 12) + basef) * esz;
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
             else if (r == 1) round32<4, DIT, MODE, KIND>(re, im, p, R0, TwSmem32{midtw + (tid & ((1u << R0) - 1u)), 1 << R0}, false, tid_odd);
             else round32<4, DIT, MODE, KIND>(re, im, p, R0 + 4, TwRegs32{uwr, uwi}, false, tid_odd);
 
-            if (last && full && !DIT && p.out_sb == 4) {
+            if (last && full && (!DIT || NR == 1) && p.out_sb == 4) {
                 // DIF results go back into the thread's own tile slots (the ones it read for this round) and
                 // leave per warp, 512 contiguous bytes per instruction (up to the run length)
 #pragma unroll
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
                     const unsigned i = warp_piece(j);
                     *reinterpret_cast<int4 *>(reinterpret_cast<int2 *>(p.out) + g0 + i) = *reinterpret_cast<const int4 *>(sm + phys8(i));
                 }
-            } else if (last && full && !DIT) {
+            } else if (last && full && (!DIT || NR == 1)) {
                 // packed 16-bit output (16-bit data with TWDL_WIDTH > 16): the packed word takes the first half of
                 // the thread's own slot; the warp then gathers four of them per 16-byte store
 #pragma unroll
@@ -679,6 +679,11 @@ template <int NLOG2, bool DIT> cudaError_t launch_contig(const Fast32Params &p, 
 template <bool DIT> cudaError_t launch_contig_n(const Fast32Params &p, int bits, int mode, int kind, int grid, cudaStream_t st)
 {
     switch (bits) {
+    case 3: return launch_contig<3, DIT>(p, mode, kind, grid, st);
+    case 4: return launch_contig<4, DIT>(p, mode, kind, grid, st);
+    case 5: return launch_contig<5, DIT>(p, mode, kind, grid, st);
+    case 6: return launch_contig<6, DIT>(p, mode, kind, grid, st);
+    case 7: return launch_contig<7, DIT>(p, mode, kind, grid, st);
     case 8: return launch_contig<8, DIT>(p, mode, kind, grid, st);
     case 9: return launch_contig<9, DIT>(p, mode, kind, grid, st);
     case 10: return launch_contig<10, DIT>(p, mode, kind, grid, st);

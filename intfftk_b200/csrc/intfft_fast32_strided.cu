@@ -11,10 +11,10 @@ int f32_launch_strided(const f32::Fast32Params &p, int g, bool dit, int mode, in
     return (int)cudaErrorInvalidValue;
 }
 
-// plans whose every intermediate fits 32-bit lanes (ROUNDING needs one carry bit) and NFFT >= 8
+// plans whose every intermediate fits 32-bit lanes (ROUNDING needs one carry bit)
 bool fast32_supported(const intfft_generics &g)
 {
-    if (!g.use_fly || g.nfft_log2 < 8) return false;
+    if (!g.use_fly || g.nfft_log2 < 3) return false;
     const int worst = g.data_width + g.format * g.nfft_log2 + ((!g.format && g.rndmode) ? 1 : 0);
     return worst <= 32;
 }

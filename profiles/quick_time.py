@@ -121,6 +121,12 @@ def wide():
         time_plan(16384, steps=3, direction=d, NFFT=12, DATA_WIDTH=32, FORMAT=0, RNDMODE=1)
         time_plan(1024, steps=3, direction=d, NFFT=16, DATA_WIDTH=24, FORMAT=1)
 
+def tiny():
+    for dw in (16, 18):
+        for n in (3, 4, 5, 6, 7):
+            for d in (0, 1):
+                time_plan(1 << (26 - n), steps=3, direction=d, NFFT=n, DATA_WIDTH=dw, FORMAT=0)
+
 def c3():
     time_plan(4096, steps=10, NFFT=16, DATA_WIDTH=24, FORMAT=1)
 
