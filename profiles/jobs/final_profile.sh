@@ -12,3 +12,5 @@ for c in c2 c3 c4 c5 c5u; do
   tail -c 200 gpurun_out/bench_r01c_$c.json
 done
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_r01c_reference.json 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.txt 2>&1; tail -2 gpurun_out/smoke.txt
+python profiles/sweep_nfft.py > gpurun_out/sweep_nfft_r01c.jsonl 2> gpurun_out/sweep.err
