@@ -84,12 +84,11 @@ void build_passes(Plan &pl)
     // n - 8 stage bits above them as one strided pass (c3: 8 strided bits on 32-bit lanes + 8 here)
     bool wide8 = false;
     if (!no_fast && g.use_fly && !f16 && !f32 && (n == 8 || (n >= 12 && n <= 16))) {
-        const int before = dit ? 0 : n - 8;
-        const int w_out = g.data_width + (before + 8) * g.format;
-        const int max_dtwc = dit ? (w_out - g.format) : w_out;
-        PassParams t{};
-        t.n = n; t.dw = g.data_width; t.format = g.format; t.cm = cm;
-        wide8 = pick_lane(w_out + rnd_extra, max_dtwc, g.twdl_width) == LANE_I64_P64 && fast64_uniform_kind(t, dit) >= 0;
+        // the plan as a whole needs 64-bit lanes with 64-bit products; each of its two passes then takes the
+        // narrowest kernel family its own widths allow (32-bit lanes where they still fit)
+        const int w_final = g.data_width + n * g.format;
+        const int max_dtwc = dit ? (w_final - g.format) : w_final;
+        wide8 = pick_lane(w_final + rnd_extra, max_dtwc, g.twdl_width) == LANE_I64_P64;
     }
     if (wide8) {
         if (n == 8) spans.push_back({0, 8, false});
@@ -144,7 +143,9 @@ void build_passes(Plan &pl)
         const bool span32 = !no_fast && g.use_fly && geom32 && kp.L == 12 && (w_out + rnd_extra) <= 32 &&
                             kp.in_sb <= 4 && kp.out_sb <= 4;
         pd.path = f16 ? 1 : ((f32 || span32) ? 2 : 0);
-        if (wide8 && !sp.strided) pd.path = 3;
+        if (wide8 && !sp.strided && pd.path == 0) pd.path = 3;
+        // the strided pass of a wide plan whose widths no longer fit 32-bit lanes: 64-bit-lane strided kernel
+        if (wide8 && sp.strided && pd.path == 0 && geom32 && kp.L == 12 && pd.lane == LANE_I64_P64) pd.path = 4;
         stages_done += sp.bits;
         pl.passes.push_back(pd);
     }
@@ -307,6 +308,8 @@ static int exec_frames(intfft_plan *p, const void *d_in, void *d_out, long long 
             e = launch_fast32(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
         else if (pd.path == 3)
             e = launch_fast64(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
+        else if (pd.path == 4)
+            e = launch_fast64_strided(pd, p->mode, dit, p->d_tw, p->num_sms, cuda_stream);
         else
             e = launch_tile_pass(pd, p->mode, dit, p->num_sms, cuda_stream);
         if (e) return INTFFT_ECUDA;

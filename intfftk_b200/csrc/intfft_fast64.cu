@@ -57,10 +57,12 @@ template <bool DIT, int MODE> __device__ __forceinline__ Stg64 stage64(const Fas
     const int dtw = p.dw + ii * FORMAT;
     st.ow = dtw + FORMAT;
     st.dtwc = DIT ? dtw : st.ow;
-    // the single arrangement is the double one without pre-shift (intfft_fast32.cuh: stage_of)
-    const bool dbl = st.dtwc >= p.cm.lim_single;
-    st.k = dbl ? p.cm.k_pre : 0;
-    st.sp = dbl ? p.cm.sh_post : p.cm.sh_single;
+    // One form covers all three arrangements: wrap(((P2 >> k) -+ (P1 >> k)) >> sp).  single: k = 0, sp = sh_single;
+    // double: k = k_pre, sp = sh_post; triple: k = sh_single, sp = 0 — its per-product wrap to dtwc bits
+    // (int_cmult_trpl18_dsp48.vhd:151-155) commutes with the subtraction, wrapping being arithmetic mod 2^dtwc
+    const bool dbl = st.dtwc >= p.cm.lim_single, trpl = st.dtwc >= p.cm.lim_dbl;
+    st.k = trpl ? p.cm.sh_single : (dbl ? p.cm.k_pre : 0);
+    st.sp = trpl ? 0 : (dbl ? p.cm.sh_post : p.cm.sh_single);
     return st;
 }
 
@@ -135,7 +137,7 @@ __device__ __forceinline__ int64_t wrap_any(int64_t v, int w)
 __device__ __forceinline__ int64_t field_any(int64_t t, int sh, int w) { return wrap_any(sra64(t, sh), w); }
 
 // KIND: 0 single, 1 double, 2 triple (the same for every multiplying stage of the pass, every width beyond 32
-// bits); 3 = single / double chosen per stage, any width (plans whose STAGE 7..0 cross the 32-bit line)
+// bits); 3 = arrangement chosen per stage, any width (plans whose STAGE 7..0 cross the 32-bit line or a limit)
 template <int KIND>
 __device__ __forceinline__ void cmul64(int64_t dr, int64_t di, int wr, int wi, const CmultConsts &cm, const Stg64 &st,
                                        int64_t &o_re, int64_t &o_im)
@@ -185,7 +187,8 @@ template <int MODE, bool ANYW = false> __device__ __forceinline__ void addsub64(
     }
 }
 
-template <bool DIT, int MODE, int KIND>
+// MUL: the caller knows st.s >= 2 (every stage of a strided top pass): no per-butterfly stage branches
+template <bool DIT, int MODE, int KIND, bool MUL = false>
 __device__ __forceinline__ void fly64(const Stg64 &st, bool odd, const CmultConsts &cm, int64_t &ar, int64_t &ai,
                                       int64_t &br, int64_t &bi, int wr, int wi)
 {
@@ -196,10 +199,10 @@ __device__ __forceinline__ void fly64(const Stg64 &st, bool odd, const CmultCons
         addsub64<MODE, KIND == 3>(ai, bi, st.ow, xi, si);
         ar = xr;
         ai = xi;
-        if (st.s == 0) {
+        if (!MUL && st.s == 0) {
             br = sr;
             bi = si;
-        } else if (st.s == 1) {
+        } else if (!MUL && st.s == 1) {
             br = odd ? si : sr;
             bi = odd ? negq64(sr) : si;
         } else {
@@ -207,10 +210,10 @@ __device__ __forceinline__ void fly64(const Stg64 &st, bool odd, const CmultCons
         }
     } else {
         T wr_, wi_;
-        if (st.s == 0) {
+        if (!MUL && st.s == 0) {
             wr_ = br;
             wi_ = bi;
-        } else if (st.s == 1) {
+        } else if (!MUL && st.s == 1) {
             wr_ = odd ? negq64(bi) : br;
             wi_ = odd ? br : bi;
         } else {                                      // multiplier fed with swapped re / im, outputs swapped back
@@ -350,6 +353,146 @@ __global__ void __launch_bounds__(256, 2) fast64_kernel(const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Strided pass on 64-bit lanes: the top G = 4 or 8 stage bits of a 2^12 / 2^16-point plan whose values have
+// outgrown 32 bits there (wide DIT plans end with it, DIF plans wider than 24 bits start with it).  Same
+// geometry as the packed-16 / 32-bit strided kernels: a tile is 2^G rows (pitch 2^(NFFT-G) samples) by
+// 2^(12-G) contiguous columns, a CTA keeps one column block and walks over frames so that the twiddles of
+// the block are fetched once.  16 samples per thread, arrangement and wrap width per stage (instance 3).
+// The single 64 KB exchange tile needs no skew: in both ownerships the lanes of a quarter-warp hold eight
+// consecutive 16-byte elements.
+struct Strided64Params {
+    const void *in;
+    void *out;
+    const int2 *tw;
+    int64_t batch;
+    int n, dw, format, in_sb, out_sb, in_wrap;
+    int frames_per_unit;
+    int64_t n_units;
+    CmultConsts cm;
+};
+
+template <int G, bool DIT, int MODE>
+__global__ void __launch_bounds__(256, 2) fast64_strided_kernel(const __grid_constant__ Strided64Params p)
+{
+    constexpr int C = 12 - G, NR = G / 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int2 *midtw = reinterpret_cast<int2 *>(smem_raw);                          // [15][16]
+    longlong2 *tile = reinterpret_cast<longlong2 *>(smem_raw + 2048);
+
+    const unsigned tid = threadIdx.x;
+    const int pb = p.n - G;
+    const unsigned cmask = (1u << C) - 1u;
+    const int mid_bits = pb - C;
+    Fast64Params sp{};                              // what stage64<> reads
+    sp.n = p.n; sp.dw = p.dw; sp.format = p.format; sp.cm = p.cm;
+
+    for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const unsigned mid = (unsigned)(u & ((1ll << mid_bits) - 1));
+        const int64_t f0 = (u >> mid_bits) * p.frames_per_unit;
+        const int64_t f1 = (f0 + p.frames_per_unit < p.batch) ? f0 + p.frames_per_unit : p.batch;
+        auto kidx = [&](unsigned l) { return ((l >> C) << pb) | (mid << C) | (l & cmask); };
+
+        int uwr[15], uwi[15];                       // round on local bits 8..11: STAGE pb + (8 + q - C)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < (1 << q); ++j) {
+                const int sgl = pb + (8 + q - C);
+                const int2 w = __ldg(p.tw + (1u << sgl) + (kidx(tid | ((unsigned)j << 8)) & ((1u << sgl) - 1u)));
+                uwr[(1 << q) - 1 + j] = w.x;
+                uwi[(1 << q) - 1 + j] = w.y;
+            }
+        if (NR == 2) {                              // round on local bits 4..7: table[w][tid & 15]
+            __syncthreads();
+            if (tid < 240) {
+                const int w = tid >> 4, lo4 = tid & 15;
+                const int q = w >= 7 ? 3 : (w >= 3 ? 2 : (w >= 1 ? 1 : 0));
+                const int j = w - ((1 << q) - 1);
+                const int sgl = pb + (4 + q - C);
+                midtw[w * 16 + lo4] = __ldg(p.tw + (1u << sgl) + (kidx((unsigned)lo4 | ((unsigned)j << 4)) & ((1u << sgl) - 1u)));
+            }
+            __syncthreads();
+        }
+
+        for (int64_t f = f0; f < f1; ++f) {
+            const int64_t gbase = (f << p.n) + ((int64_t)mid << C);
+            int64_t re[16], im[16];
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) {
+                const int r = DIT ? rr : NR - 1 - rr;
+                const int lo = 12 - 4 * (NR - r);
+                const bool first = rr == 0, last = rr == NR - 1;
+                const unsigned base = (tid & ((1u << lo) - 1u)) | ((tid >> lo) << (lo + 4));
+                // register m sits 2^(lo-C) m rows below register 0 (lo >= C in every geometry)
+                const int64_t g0 = gbase + ((int64_t)(base >> C) << pb) + (base & cmask);
+                const int64_t gstep = (int64_t)1 << (pb + lo - C);
+                if (first) {
+                    if (p.in_sb == 4) {
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) { const int2 v = __ldg(reinterpret_cast<const int2 *>(p.in) + g0 + m * gstep); re[m] = v.x; im[m] = v.y; }
+                    } else if (p.in_sb == 8) {
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) { const longlong2 v = __ldg(reinterpret_cast<const longlong2 *>(p.in) + g0 + m * gstep); re[m] = v.x; im[m] = v.y; }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) { const short2 v = __ldg(reinterpret_cast<const short2 *>(p.in) + g0 + m * gstep); re[m] = v.x; im[m] = v.y; }
+                    }
+                    if (p.in_wrap) {
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) { re[m] = wrapw<int64_t>(re[m], p.dw); im[m] = wrapw<int64_t>(im[m], p.dw); }
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) { const longlong2 v = tile[base + ((unsigned)m << lo)]; re[m] = v.x; im[m] = v.y; }
+                }
+                // ---- four multiplying stages on the register bits ----
+                const int s0 = pb + (lo - C);
+#pragma unroll
+                for (int step = 0; step < 4; ++step) {
+                    const int q = DIT ? step : 3 - step;
+                    const Stg64 st = stage64<DIT, MODE>(sp, s0 + q);
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        if (m & (1 << q)) continue;
+                        const int w = (1 << q) - 1 + (m & ((1 << q) - 1));
+                        int wr, wi;
+                        if (lo == 8) { wr = uwr[w]; wi = uwi[w]; }
+                        else { const int2 t = midtw[w * 16 + (tid & 15u)]; wr = t.x; wi = t.y; }
+                        fly64<DIT, MODE, 3, true>(st, false, p.cm, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi);
+                    }
+                }
+                if (last) {
+                    if (p.out_sb == 8) {
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) reinterpret_cast<longlong2 *>(p.out)[g0 + m * gstep] = make_longlong2(re[m], im[m]);
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) reinterpret_cast<int2 *>(p.out)[g0 + m * gstep] = make_int2((int)re[m], (int)im[m]);
+                    }
+                } else {
+                    __syncthreads();                                   // the previous frame's readers have left the tile
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) tile[base + ((unsigned)m << lo)] = make_longlong2(re[m], im[m]);
+                    __syncthreads();
+                }
+            }
+        }
+    }
+}
+
+template <int G, bool DIT> cudaError_t launch_strided64_k(const Strided64Params &p, int mode, int grid, cudaStream_t st)
+{
+    using K = void (*)(const Strided64Params);
+    K k = mode == MODE_TRUNC ? (K)fast64_strided_kernel<G, DIT, MODE_TRUNC>
+        : (mode == MODE_ROUND ? (K)fast64_strided_kernel<G, DIT, MODE_ROUND> : (K)fast64_strided_kernel<G, DIT, MODE_UNSCALED>);
+    const int smem = 2048 + 4096 * 16;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 template <bool DIT, int MODE> cudaError_t launch_k(const Fast64Params &p, int kind, int grid, cudaStream_t st)
 {
     using K = void (*)(const Fast64Params);
@@ -367,13 +510,12 @@ template <bool DIT, int MODE> cudaError_t launch_k(const Fast64Params &p, int ki
 }  // namespace
 
 // Which instance runs STAGE 7..0 of this plan: 1 / 2 when every stage of the pass is wider than 32 bits and all
-// multiplying stages (STAGE 2..7) share the double / triple arrangement; 3 (per-stage single / double, any
-// width) when some stage still wraps at <= 32 bits or the arrangements differ; -1 when a triple stage is mixed
-// with others (left to the generic kernel).
+// multiplying stages (STAGE 2..7) share the double / triple arrangement; 3 (arrangement per stage, any width)
+// when some stage still wraps at <= 32 bits or the arrangements differ.
 int fast64_uniform_kind(const PassParams &kp, bool dit)
 {
     int kind = -1;
-    bool all_wide = true, uniform = true, any_triple = false;
+    bool all_wide = true, uniform = true;
     for (int s = 0; s < 8; ++s) {
         const int ii = dit ? s : kp.n - 1 - s;
         const int dtw = kp.dw + ii * kp.format;
@@ -381,12 +523,11 @@ int fast64_uniform_kind(const PassParams &kp, bool dit)
         if (dtwc <= 32 || dtw + kp.format <= 32) all_wide = false;
         if (s < 2) continue;
         const int k = dtwc < kp.cm.lim_single ? 0 : (dtwc < kp.cm.lim_dbl ? 1 : 2);
-        if (k == 2) any_triple = true;
         if (kind >= 0 && k != kind) uniform = false;
         kind = k;
     }
     if (all_wide && uniform && kind >= 1) return kind;
-    return any_triple ? -1 : 3;
+    return 3;
 }
 
 int launch_fast64(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
@@ -422,6 +563,40 @@ int launch_fast64(const PassDesc &pd, int mode, bool dit, const int2 *tw, const 
     case MODE_UNSCALED * 2 + 0: e = launch_k<false, MODE_UNSCALED>(p, kind, (int)grid, st); break;
     default: e = launch_k<true, MODE_UNSCALED>(p, kind, (int)grid, st); break;
     }
+    count_launch();
+    return (int)e;
+}
+
+// top-bits pass of a wide plan on 64-bit lanes: kp.g in {4, 8}, kp.pb = NFFT - kp.g, every stage multiplies
+int launch_fast64_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw, int num_sms, void *stream)
+{
+    Strided64Params p{};
+    p.in = pd.kp.in;
+    p.out = pd.kp.out;
+    p.tw = tw;
+    p.n = pd.kp.n;
+    p.batch = pd.kp.total >> pd.kp.n;
+    p.dw = pd.kp.dw;
+    p.format = pd.kp.format;
+    p.in_sb = pd.kp.in_sb;
+    p.out_sb = pd.kp.out_sb;
+    p.in_wrap = pd.kp.in_wrap;
+    p.cm = pd.kp.cm;
+    const int G = pd.kp.g, C = 12 - G, mid_bits = p.n - G - C;
+    const int64_t mids = (int64_t)1 << mid_bits;
+    int64_t grid = 2ll * num_sms;
+    int64_t chunks = (8 * grid + mids - 1) / mids;
+    if (chunks < 1) chunks = 1;
+    if (chunks > p.batch) chunks = p.batch;
+    p.frames_per_unit = (int)((p.batch + chunks - 1) / chunks);
+    chunks = (p.batch + p.frames_per_unit - 1) / p.frames_per_unit;
+    p.n_units = mids * chunks;
+    if (grid > p.n_units) grid = p.n_units;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (G == 4) e = dit ? launch_strided64_k<4, true>(p, mode, (int)grid, st) : launch_strided64_k<4, false>(p, mode, (int)grid, st);
+    else if (G == 8) e = dit ? launch_strided64_k<8, true>(p, mode, (int)grid, st) : launch_strided64_k<8, false>(p, mode, (int)grid, st);
+    else e = cudaErrorInvalidValue;
     count_launch();
     return (int)e;
 }

@@ -56,7 +56,8 @@ struct PassDesc {
     int threads;
     size_t smem_bytes;
     int scratch_in, scratch_out;  // -1 = user buffer, else index of plan scratch buffer
-    int path;              // 0 generic tile kernel, 1 packed-16 kernels, 2 32-bit-lane kernels, 3 64-bit-lane low-8 kernel
+    int path;              // 0 generic tile kernel, 1 packed-16 kernels, 2 32-bit-lane kernels, 3 64-bit-lane low-8 kernel,
+                           // 4 64-bit-lane strided kernel
     int natural = 0;       // exec time: this (single, 4096-point packed-16 DIF) pass also applies int_bitrev_order
 };
 
@@ -91,6 +92,7 @@ int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const 
                   int num_sms, void *stream);
 // 64-bit-lane kernel for the lowest eight stage bits (intfft_fast64.cu)
 int fast64_uniform_kind(const PassParams &kp, bool dit);
+int launch_fast64_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw, int num_sms, void *stream);
 int launch_fast64(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
                   int num_sms, void *stream);
 int launch_bypass(const void *in, void *out, long long n_scalars, int in_sb, int out_sb, int dw,

@@ -171,7 +171,9 @@ LANE64 = [  # (nfft, dw, tw, xser, fmt, rnd): plans whose STAGE 7..0 run on the 
     # STAGE 7..0 crossing the 32-bit line and / or mixing single and double arrangements: the per-stage instance
     (12, 24, 16, "NEW", 1, 0), (12, 27, 16, "NEW", 1, 0), (12, 31, 16, "OLD", 1, 0), (8, 28, 16, "NEW", 1, 0),
     (16, 18, 16, "NEW", 1, 0), (16, 20, 17, "OLD", 1, 0), (12, 32, 16, "NEW", 0, 1), (8, 30, 20, "NEW", 1, 0),
-    (12, 22, 18, "NEW", 1, 0), (8, 32, 16, "OLD", 0, 1), (12, 26, 24, "NEW", 1, 0)]
+    (12, 22, 18, "NEW", 1, 0), (8, 32, 16, "OLD", 0, 1), (12, 26, 24, "NEW", 1, 0),
+    # double and triple arrangements inside STAGE 7..0 (the IFFT of c3's spectrum: 40 -> 56 bits)
+    (16, 40, 16, "NEW", 1, 0), (8, 41, 16, "NEW", 1, 0), (12, 38, 16, "OLD", 1, 0), (8, 34, 20, "NEW", 1, 0)]
 
 
 @pytest.mark.parametrize("nfft,dw,tw,xser,fmt,rnd", LANE64)
