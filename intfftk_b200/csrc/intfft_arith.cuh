@@ -18,11 +18,12 @@ template <typename T> struct LaneBits;
 template <> struct LaneBits<int32_t> { static constexpr int bits = 32; using U = uint32_t; };
 template <> struct LaneBits<int64_t> { static constexpr int bits = 64; using U = uint64_t; };
 
-// keep the low w bits, sign-extended (a VHDL slice).  bfe.s32 with a register length is one SGXT.
+// keep the low w bits, sign-extended (a VHDL slice): szext is one SGXT (bfe.s32 with a register length is
+// PRMT + SHF + SGXT).
 __device__ __forceinline__ int32_t sgxt32(int32_t v, int w)
 {
     int32_t r;
-    asm("bfe.s32 %0, %1, 0, %2;" : "=r"(r) : "r"(v), "r"(w));
+    asm("szext.clamp.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(w));      // one SGXT; w >= 32 copies v
     return r;
 }
 template <typename T> __device__ __forceinline__ T wrapw(T v, int w);

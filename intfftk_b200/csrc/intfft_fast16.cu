@@ -93,9 +93,9 @@ __device__ __forceinline__ void unpack(uint32_t x, int dw, int &re, int &im)
     if (DW16) {
         re = sext_lo16(x);
         im = sra<16>((int)x);
-    } else {                                   // wrap to DATA_WIDTH bits (conv_std_logic_vector)
-        re = (int)(x << (32 - dw)) >> (32 - dw);
-        im = (int)(x << (16 - dw)) >> (32 - dw);
+    } else {                                   // wrap to DATA_WIDTH bits (conv_std_logic_vector): one SGXT each
+        asm("szext.clamp.s32 %0, %1, %2;" : "=r"(re) : "r"((int)x), "r"(dw));
+        asm("szext.clamp.s32 %0, %1, %2;" : "=r"(im) : "r"((int)(x >> 16)), "r"(dw));
     }
 }
 
@@ -115,7 +115,10 @@ template <bool DW16> __device__ __forceinline__ int rnd_dif(int sum, int b, int 
 {
     int d;
     asm("mad.lo.s32 %0, %1, -1, %2;" : "=r"(d) : "r"(b), "r"(sum));
-    return DW16 ? sext_lo16((uint32_t)d) : ((int)((unsigned)d << sh_full) >> sh_full);
+    if (DW16) return sext_lo16((uint32_t)d);
+    int r;
+    asm("szext.clamp.s32 %0, %1, %2;" : "=r"(r) : "r"(d), "r"(32 - sh_full));      // sh_full = 32 - DATA_WIDTH
+    return r;
 }
 
 template <bool DIT, bool DW16, int MODE, bool RAWY = false>

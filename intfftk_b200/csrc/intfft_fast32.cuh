@@ -88,7 +88,7 @@ __device__ __forceinline__ int field(long long t, int sh, int w)
     return hi >> (32 - w);
 }
 // low w bits of a 32-bit value, sign-extended
-__device__ __forceinline__ int sx(int v, int w) { return (int)((unsigned)v << (32 - w)) >> (32 - w); }
+__device__ __forceinline__ int sx(int v, int w) { return sgxt32(v, w); }      // one SGXT (intfft_arith.cuh)
 
 // exact signed 32 x 32 -> 64 (asm: next to word-wise shifts the front end otherwise emits IMAD.WIDE.U32 + fix-ups)
 __device__ __forceinline__ long long mulw(int a, int b)

@@ -68,8 +68,8 @@ template <bool DIT, int MODE> __device__ __forceinline__ Stg64 stage64(const Fas
 
 // register pairs are split / joined with mov.b64: built from shifts and ORs, the front end no longer sees a
 // plain pair and spends five or six instructions on every 64-bit add that follows
-__device__ __forceinline__ unsigned lo32(int64_t v) { unsigned lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); (void)hi; return lo; }
-__device__ __forceinline__ int hi32(int64_t v) { unsigned lo; int hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); (void)lo; return hi; }
+__device__ __forceinline__ unsigned lo32(int64_t v) { return (unsigned)v; }
+__device__ __forceinline__ int hi32(int64_t v) { return (int)(v >> 32); }
 __device__ __forceinline__ int64_t mk64(unsigned lo, int hi) { int64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
 
 // d = hi * 2^32 + (int)lo with hi corrected for the sign of the low word
@@ -116,7 +116,7 @@ __device__ __forceinline__ int64_t sra64(int64_t t, int sh)
 // keep the low w bits of v, sign-extended, 32 < w <= 64
 __device__ __forceinline__ int64_t wrap_hi(int64_t v, int w)
 {
-    return mk64(lo32(v), (int)((unsigned)hi32(v) << (64 - w)) >> (64 - w));
+    return mk64(lo32(v), sgxt32(hi32(v), w - 32));
 }
 // bits [sh + w - 1 : sh] of t, sign-extended; 0 <= sh < 32 < w, sh + w <= 64 (all grid-uniform)
 __device__ __forceinline__ int64_t field64(int64_t t, int sh, int w)
@@ -128,13 +128,58 @@ __device__ __forceinline__ int64_t field64(int64_t t, int sh, int w)
 // sign-extended from min(w, 32) bits, the high word from w - 32 bits or taken from the low word's sign
 __device__ __forceinline__ int64_t wrap_any(int64_t v, int w)
 {
-    const int s1 = w >= 32 ? 0 : 32 - w, s2 = w > 32 ? 64 - w : 0;
-    const int lo = (int)(lo32(v) << s1) >> s1;
-    const int hi_w = (int)((unsigned)hi32(v) << s2) >> s2;
+    const int lo = sgxt32((int)lo32(v), w);                      // w >= 32: unchanged
+    const int hi_w = sgxt32(hi32(v), w > 32 ? w - 32 : 32);
     return mk64((unsigned)lo, w > 32 ? hi_w : (lo >> 31));
 }
-// bits [sh + w - 1 : sh] of t, sign-extended, 0 <= sh < 32, any w with sh + w <= 64
-__device__ __forceinline__ int64_t field_any(int64_t t, int sh, int w) { return wrap_any(sra64(t, sh), w); }
+
+// The double / per-stage arrangements work on explicit half-word pairs with carry chains: as int64_t the
+// intermediate values had to be re-joined into aligned register pairs after every word-wise shift, which cost
+// two to three moves per butterfly.
+struct W2 {
+    unsigned lo;
+    int hi;                  // value = hi * 2^32 + lo
+};
+__device__ __forceinline__ W2 mulx(const Split &d, int w)
+{
+    const int64_t t = mulw(d.lo, w);
+    W2 r;
+    r.lo = lo32(t);
+    r.hi = hi32(t) + d.hi * w;
+    return r;
+}
+__device__ __forceinline__ W2 srax(W2 a, int k)        // 0 <= k < 32
+{
+    W2 r;
+    r.lo = __funnelshift_r(a.lo, (unsigned)a.hi, k);
+    r.hi = a.hi >> k;
+    return r;
+}
+__device__ __forceinline__ W2 subx(W2 a, W2 b)
+{
+    W2 r;
+    asm("sub.cc.u32 %0, %2, %4;\n\tsubc.u32 %1, %3, %5;" : "=r"(r.lo), "=r"(r.hi) : "r"(a.lo), "r"(a.hi), "r"(b.lo), "r"(b.hi));
+    return r;
+}
+__device__ __forceinline__ W2 addx(W2 a, W2 b)
+{
+    W2 r;
+    asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=r"(r.lo), "=r"(r.hi) : "r"(a.lo), "r"(a.hi), "r"(b.lo), "r"(b.hi));
+    return r;
+}
+// bits [sh + w - 1 : sh] of t, sign-extended; 0 <= sh < 32 < w
+__device__ __forceinline__ int64_t fieldx(W2 t, int sh, int w)
+{
+    return mk64(__funnelshift_r(t.lo, (unsigned)t.hi, sh), sgxt32(t.hi >> sh, w - 32));
+}
+// the same for any 2 <= w <= 64 (branch-free)
+__device__ __forceinline__ int64_t fieldx_any(W2 t, int sh, int w)
+{
+    const W2 v = srax(t, sh);
+    const int lo = sgxt32((int)v.lo, w);                          // w >= 32: unchanged
+    const int hi_w = sgxt32(v.hi, w > 32 ? w - 32 : 32);
+    return mk64((unsigned)lo, w > 32 ? hi_w : (lo >> 31));
+}
 
 // KIND: 0 single, 1 double, 2 triple (the same for every multiplying stage of the pass, every width beyond 32
 // bits); 3 = arrangement chosen per stage, any width (plans whose STAGE 7..0 cross the 32-bit line or a limit)
@@ -145,20 +190,20 @@ __device__ __forceinline__ void cmul64(int64_t dr, int64_t di, int wr, int wi, c
     const int dtwc = st.dtwc;
     const Split r = split64(dr), i = split64(di);
     if (KIND == 3) {
-        const int64_t tr = sra64(mul64x32(r, wr), st.k) - sra64(mul64x32(i, wi), st.k);
-        const int64_t ti = sra64(mul64x32(r, wi), st.k) + sra64(mul64x32(i, wr), st.k);
-        o_re = field_any(tr, st.sp, dtwc);
-        o_im = field_any(ti, st.sp, dtwc);
+        const W2 tr = subx(srax(mulx(r, wr), st.k), srax(mulx(i, wi), st.k));
+        const W2 ti = addx(srax(mulx(r, wi), st.k), srax(mulx(i, wr), st.k));
+        o_re = fieldx_any(tr, st.sp, dtwc);
+        o_im = fieldx_any(ti, st.sp, dtwc);
     } else if (KIND == 0) {
         const int64_t tr = mad64x32(i, -wi, mul64x32(r, wr));
         const int64_t ti = mad64x32(i, wr, mul64x32(r, wi));
         o_re = field64(tr, cm.sh_single, dtwc);
         o_im = field64(ti, cm.sh_single, dtwc);
     } else if (KIND == 1) {
-        const int64_t tr = sra64(mul64x32(r, wr), cm.k_pre) - sra64(mul64x32(i, wi), cm.k_pre);
-        const int64_t ti = sra64(mul64x32(r, wi), cm.k_pre) + sra64(mul64x32(i, wr), cm.k_pre);
-        o_re = field64(tr, cm.sh_post, dtwc);
-        o_im = field64(ti, cm.sh_post, dtwc);
+        const W2 tr = subx(srax(mulx(r, wr), cm.k_pre), srax(mulx(i, wi), cm.k_pre));
+        const W2 ti = addx(srax(mulx(r, wi), cm.k_pre), srax(mulx(i, wr), cm.k_pre));
+        o_re = fieldx(tr, cm.sh_post, dtwc);
+        o_im = fieldx(ti, cm.sh_post, dtwc);
     } else {
         const int64_t a = field64(mul64x32(r, wr), cm.sh_single, dtwc), b = field64(mul64x32(i, wi), cm.sh_single, dtwc);
         const int64_t c = field64(mul64x32(r, wi), cm.sh_single, dtwc), d = field64(mul64x32(i, wr), cm.sh_single, dtwc);
