@@ -17,6 +17,8 @@
 // half-warp (__syncwarp), B <-> C goes through a skewed shared tile under CTA barriers.
 // Arithmetic = intfft_fast32.cuh (fly32 / cmul32): int_dif2_fly.vhd:142-373, int_dit2_fly.vhd:140-325,
 // int_cmult_dsp48.vhd:182-190 / 307-317 and the dbl18 / dbl35 arrangements.
+#include <type_traits>
+
 #include "intfft_fast32.cuh"
 
 namespace intfft {
@@ -182,19 +184,24 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
                 round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
             }
             // ---- STAGE 12 between the parked lower half and the registers; coalesced stores ----
+            auto stage12 = [&](auto out_sb_tag) {       // the container size is tested once per frame, not per store
+                constexpr int OSB = decltype(out_sb_tag)::value;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int4 a = ownS[j];
+                for (int j = 0; j < 8; ++j) {
+                    const int4 a = ownS[j];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int m = 2 * j + e;
-                    const int2 w = __ldg(twD + 256 * m);
-                    V xr = mk(e ? a.z : a.x), xi = mk(e ? a.w : a.y);
-                    fly32<DIT, MODE, KIND>(stD, false, p.cm, xr, xi, re[m], im[m], w.x, w.y);
-                    st_sample(p.out, g0 + tid + 256u * m, p.out_sb, xr.f, xi.f);
-                    st_sample(p.out, g0 + 4096 + tid + 256u * m, p.out_sb, re[m].f, im[m].f);
+                    for (int e = 0; e < 2; ++e) {
+                        const int m = 2 * j + e;
+                        const int2 w = __ldg(twD + 256 * m);
+                        V xr = mk(e ? a.z : a.x), xi = mk(e ? a.w : a.y);
+                        fly32<DIT, MODE, KIND>(stD, false, p.cm, xr, xi, re[m], im[m], w.x, w.y);
+                        st_sample(p.out, g0 + tid + 256u * m, OSB, xr.f, xi.f);
+                        st_sample(p.out, g0 + 4096 + tid + 256u * m, OSB, re[m].f, im[m].f);
+                    }
                 }
-            }
+            };
+            if (p.out_sb == 4) stage12(std::integral_constant<int, 4>{});
+            else stage12(std::integral_constant<int, 2>{});
         } else {
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
 (timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/c53_pytest.txt 2>&1
 tail -3 gpurun_out/c53_pytest.txt
-python profiles/quick_time.py others modes_mini > gpurun_out/c53_quick.txt 2>&1
+python profiles/quick_time.py others > gpurun_out/c53_quick.txt 2>&1
 cat gpurun_out/c53_quick.txt
