@@ -274,7 +274,7 @@ def main():
             "config": {"workload": desc, "generics": gk, "direction": "DIF" if direction == 0 else "DIT",
                        "batch_per_gpu": batch, "parallelism": f"batch-split x{world}",
                        "l2": f"inputs larger than L2 ({lay.in_bytes >> 20} MiB in + {lay.out_bytes >> 20} MiB out per step)",
-                       "kernels_per_step": lay.n_passes},
+                       "kernels_per_step": lay.n_passes, "kernel_chain": ib.describe(g, batch, direction)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": known_traffic(args.config), "peak_source": peak_src,
                          "algorithmic_bytes_per_step": alg_bytes},

@@ -31,6 +31,7 @@
 #ifndef INTFFT_H_
 #define INTFFT_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -132,6 +133,12 @@ int intfft_fill_random(void *d_buf, int64_t n_scalars, int scalar_bytes, int wid
 /* 64-bit order-sensitive checksum of a device buffer of scalars (sum of value * odd hash(index)). */
 int intfft_checksum(const void *d_buf, int64_t n_scalars, int scalar_bytes,
                     uint64_t *h_sum, int device, void *cuda_stream);
+
+/* Which kernels a plan for these generics would run, as text ("fast32_strided[bits 8..15] -> fast64[bits 0..7,
+ * instance 1]"), written to buf (at most len bytes, NUL-terminated).  Host-only, needs no device: the stand-in for
+ * reading the elaboration log of the reference (which multiplier / delay-line variants were generated), and
+ * what the CPU test suite uses to pin the kernel selection of every BASELINE configuration. */
+int intfft_describe(const intfft_generics *g, int64_t batch, char *buf, size_t len);
 
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t intfft_launch_count(void);

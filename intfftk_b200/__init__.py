@@ -6,7 +6,7 @@ becomes a `Core` bound to the C-ABI in include/intfft.h.  PyTorch is used only f
 streams.  There is no CPU fallback: importing `core` loads libintfft_b200.so or raises.
 """
 from .core import (Core, Pair, Generics, IntfftError, int_fftNk, int_ifftNk, set_mode, lib, twiddles, validate,
-                   bitrev_order, fill_random, checksum, launch_count, shard_range)
+                   bitrev_order, fill_random, checksum, launch_count, shard_range, describe)
 
 __all__ = ["Core", "Pair", "Generics", "IntfftError", "int_fftNk", "int_ifftNk", "set_mode", "lib", "twiddles",
-           "validate", "bitrev_order", "fill_random", "checksum", "launch_count", "shard_range"]
+           "validate", "bitrev_order", "fill_random", "checksum", "launch_count", "shard_range", "describe"]

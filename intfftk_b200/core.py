@@ -65,6 +65,7 @@ def lib() -> ctypes.CDLL:
         L.intfft_fill_random.argtypes = [vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
                                          ctypes.c_int, vp]
         L.intfft_checksum.argtypes = [vp, ctypes.c_int64, ctypes.c_int, P(ctypes.c_uint64), ctypes.c_int, vp]
+        L.intfft_describe.argtypes = [P(_CGenerics), ctypes.c_int64, ctypes.c_char_p, ctypes.c_size_t]
         L.intfft_launch_count.restype = ctypes.c_int64
         L.intfft_strerror.restype = ctypes.c_char_p
         L.intfft_strerror.argtypes = [ctypes.c_int]
@@ -259,6 +260,16 @@ class Pair:
 def _torch_dtype(np_dtype):
     import torch
     return {np.int16: torch.int16, np.int32: torch.int32, np.int64: torch.int64}[np_dtype]
+
+
+def describe(generics: Generics, batch: int = 1, direction: int = 0) -> str:
+    """Kernel chain a plan for these generics would run (host-only; no device needed)."""
+    buf = ctypes.create_string_buffer(512)
+    c = generics.c_struct(direction)
+    st = lib().intfft_describe(ctypes.byref(c), batch, buf, len(buf))
+    if st:
+        raise IntfftError(st, "intfft_describe")
+    return buf.value.decode()
 
 
 def int_fftNk(batch: int, device: int = 0, **generics) -> Core:

@@ -3,9 +3,11 @@
 // intfft_fast16.cu and intfft_util.cu.  There is no CPU compute path in this file.
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "intfft_internal.h"
@@ -512,6 +514,46 @@ int intfft_checksum(const void *d_buf, int64_t n_scalars, int sb, uint64_t *h_su
     if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = INTFFT_ECUDA;
     cudaFree(d_sum);
     return rc;
+}
+
+int intfft_describe(const intfft_generics *g, int64_t batch, char *buf, size_t len)
+{
+    if (!g || !buf || len == 0 || batch < 1) return INTFFT_EINVAL;
+    const int st = validate(g);
+    if (st) return st;
+    Plan pl;                                   // host-side description only: nothing is allocated on a device
+    pl.g = *g;
+    pl.batch = batch;
+    pl.mode = g->format ? MODE_UNSCALED : (g->rndmode ? MODE_ROUND : MODE_TRUNC);
+    pl.in_width = g->data_width;
+    pl.out_width = g->data_width + g->format * g->nfft_log2;
+    pl.in_sb = scalar_bytes(pl.in_width);
+    pl.out_sb = scalar_bytes(pl.out_width);
+    std::string out;
+    if (!g->use_fly) {
+        out = "bypass";
+    } else {
+        build_passes(pl);
+        const bool dit = g->direction != 0;
+        for (size_t i = 0; i < pl.passes.size(); ++i) {
+            const PassDesc &pd = pl.passes[i];
+            const PassParams &kp = pd.kp;
+            const bool strided = kp.c > 0;
+            const char *fam = "tile";
+            char extra[48] = "";
+            if (pd.path == 1) fam = strided ? "fast16_strided" : "fast16";
+            else if (pd.path == 2) fam = strided ? "fast32_strided" : (kp.g == 13 ? "fast32_n13" : "fast32");
+            else if (pd.path == 3) { fam = "fast64"; std::snprintf(extra, sizeof extra, ", instance %d", fast64_uniform_kind(kp, dit)); }
+            else if (pd.path == 4) fam = "fast64_strided";
+            else std::snprintf(extra, sizeof extra, ", lane %d", pd.lane == LANE_I32_P64 ? 32 : (pd.lane == LANE_I64_P64 ? 64 : 128));
+            char item[128];
+            std::snprintf(item, sizeof item, "%s%s[bits %d..%d, %d->%d B%s]", i ? " -> " : "", fam, kp.pb, kp.pb + kp.g - 1,
+                          2 * kp.in_sb, 2 * kp.out_sb, extra);
+            out += item;
+        }
+    }
+    std::snprintf(buf, len, "%s", out.c_str());
+    return INTFFT_OK;
 }
 
 int64_t intfft_launch_count(void) { return (int64_t)launches(); }

@@ -94,3 +94,52 @@ def test_mode_strings_and_generics_mirror():
     assert g.out_width == 40
     c = g.c_struct(1)
     assert (c.nfft_log2, c.data_width, c.twdl_width, c.format, c.xser, c.direction) == (16, 24, 16, 1, 1, 1)
+
+
+# ---- host logic: which kernels a plan runs (intfft_describe needs no device) --------------------------------
+PLAN_CHAINS = [
+    # BASELINE configurations
+    (dict(NFFT=12, DATA_WIDTH=16, FORMAT=0), 0, ["fast16[bits 0..11"]),
+    (dict(NFFT=16, DATA_WIDTH=24, FORMAT=1), 0, ["fast32_strided[bits 8..15", "fast64[bits 0..7", "instance 1"]),
+    (dict(NFFT=20, DATA_WIDTH=16, FORMAT=0), 0, ["fast16_strided[bits 12..19", "fast16[bits 0..11"]),
+    (dict(NFFT=13, DATA_WIDTH=18, FORMAT=0), 1, ["fast32_n13[bits 0..12"]),
+    (dict(NFFT=13, DATA_WIDTH=18, FORMAT=1), 1, ["fast32_n13[bits 0..12"]),
+    # every size class of the 16-bit scaled family, both directions
+    (dict(NFFT=3, DATA_WIDTH=16, FORMAT=0), 0, ["fast16[bits 0..2"]),
+    (dict(NFFT=7, DATA_WIDTH=12, FORMAT=0, RNDMODE=1), 1, ["fast16[bits 0..6"]),
+    (dict(NFFT=13, DATA_WIDTH=16, FORMAT=0), 0, ["fast16_strided[bits 9..12", "fast16[bits 0..8"]),
+    (dict(NFFT=16, DATA_WIDTH=16, FORMAT=0), 1, ["fast16[bits 0..11", "fast16_strided[bits 12..15"]),
+    (dict(NFFT=17, DATA_WIDTH=14, FORMAT=0), 0, ["fast16_strided[bits 9..16", "fast16[bits 0..8"]),
+    # 32-bit lanes: wider data, wider twiddles, unscaled growth that still fits
+    (dict(NFFT=5, DATA_WIDTH=18, FORMAT=0), 0, ["fast32[bits 0..4"]),
+    (dict(NFFT=12, DATA_WIDTH=16, TWDL_WIDTH=18, FORMAT=0), 0, ["fast32[bits 0..11, 4->4 B"]),
+    (dict(NFFT=12, DATA_WIDTH=16, FORMAT=1), 0, ["fast32[bits 0..11, 4->8 B"]),
+    (dict(NFFT=18, DATA_WIDTH=20, FORMAT=0), 1, ["fast32[bits 0..9", "fast32_strided[bits 10..17"]),
+    # wide plans: every pass on the narrowest lane family its widths allow
+    (dict(NFFT=12, DATA_WIDTH=24, FORMAT=1), 0, ["fast32_strided[bits 8..11", "fast64[bits 0..7", "instance 3"]),
+    (dict(NFFT=12, DATA_WIDTH=24, FORMAT=1), 1, ["fast32[bits 0..7", "fast64_strided[bits 8..11"]),
+    (dict(NFFT=16, DATA_WIDTH=18, FORMAT=1), 0, ["fast32_strided[bits 8..15", "fast64[bits 0..7", "instance 3"]),
+    (dict(NFFT=16, DATA_WIDTH=36, FORMAT=0), 0, ["fast64_strided[bits 8..15", "fast64[bits 0..7", "instance 1"]),
+    (dict(NFFT=8, DATA_WIDTH=45, FORMAT=0), 0, ["fast64[bits 0..7", "instance 2"]),
+    # beyond 64-bit products, or geometries without a specialised kernel: the generic tile kernel
+    (dict(NFFT=16, DATA_WIDTH=40, FORMAT=1), 1, ["tile[", "lane 128"]),
+    (dict(NFFT=10, DATA_WIDTH=24, FORMAT=1), 0, ["tile[bits 0..9", "lane 64"]),
+    (dict(NFFT=12, DATA_WIDTH=16, FORMAT=0, USE_FLY=0), 0, ["bypass"]),
+]
+
+
+@pytest.mark.parametrize("kw,direction,expect", PLAN_CHAINS)
+def test_kernel_selection_is_pinned(kw, direction, expect):
+    text = ib.describe(ib.Generics(**kw), 8, direction)
+    pos = 0
+    for piece in expect:                       # the pieces appear in this order
+        at = text.find(piece, pos)
+        assert at >= 0, f"{kw} dir={direction}: expected {piece!r} in {text!r}"
+        pos = at + 1
+
+
+def test_describe_rejects_what_does_not_elaborate():
+    with pytest.raises(ib.IntfftError):
+        ib.describe(ib.Generics(NFFT=12, DATA_WIDTH=16, TWDL_WIDTH=30), 1, 0)
+    with pytest.raises(ib.IntfftError):
+        ib.describe(ib.Generics(NFFT=12, DATA_WIDTH=16, FORMAT=1, RNDMODE=1), 1, 0)
