@@ -255,6 +255,21 @@ __device__ __forceinline__ void round32(V (&re)[16], V (&im)[16], const Fast32Pa
     for (int step = 0; step < R; ++step) {
         const int q = DIT ? step : R - 1 - step;
         const Stg st = stage_of<DIT, MODE, KIND>(p, s0 + q);
+        // A mixed pass still has stages on the single arrangement (c3's first pass: 3 of 8): those take the
+        // single code — products accumulated in one IMAD.WIDE chain, no per-product pre-shift, 12 instructions
+        // fewer per butterfly — behind a grid-uniform branch around the stage's eight butterflies.
+        if (KIND == KIND_MIXED && st.kind == 0) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                if (m & (1 << q)) continue;
+                const int w = (1 << q) - 1 + (m & ((1 << q) - 1));
+                int wr = 0, wi = 0;
+                if (MUL || st.s >= 2) tw(w, wr, wi);
+                const bool odd = lo_is_zero ? ((m & 1) != 0) : tid_odd;
+                fly32<DIT, MODE, KIND_SINGLE, MUL>(st, odd, p.cm, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi);
+            }
+            continue;
+        }
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
             if (m & (1 << q)) continue;
