@@ -92,6 +92,21 @@ def test_parity_packed16_kernel_widths(ib, oracle, nfft, direction):
         assert np.array_equal(got, want), (dw, tw, xser)
 
 
+@pytest.mark.parametrize("nfft", [3, 4, 5, 6, 7])
+@pytest.mark.parametrize("direction", [0, 1])
+def test_parity_tiny_frames_all_width_classes(ib, oracle, nfft, direction):
+    """8..128-point frames on the specialised kernels: packed-16 with DATA_WIDTH < 16 and a narrow twiddle,
+    32-bit lanes (scaled, rounding, unscaled growth, packed 16-bit in / 32-bit out), ragged last tile."""
+    cases = [dict(DATA_WIDTH=12, TWDL_WIDTH=14, FORMAT=0, RNDMODE=0), dict(DATA_WIDTH=9, TWDL_WIDTH=16, FORMAT=0, RNDMODE=1),
+             dict(DATA_WIDTH=18, TWDL_WIDTH=16, FORMAT=0, RNDMODE=0), dict(DATA_WIDTH=24, TWDL_WIDTH=18, FORMAT=0, RNDMODE=1),
+             dict(DATA_WIDTH=20, TWDL_WIDTH=16, FORMAT=1, RNDMODE=0), dict(DATA_WIDTH=16, TWDL_WIDTH=16, FORMAT=1, RNDMODE=0),
+             dict(DATA_WIDTH=16, TWDL_WIDTH=20, FORMAT=0, RNDMODE=0)]
+    for kw in cases:
+        batch = (9000 >> nfft) + 3
+        got, want = _run_both(ib, oracle, batch, seed=nfft * 11 + direction, via="device", NFFT=nfft, direction=direction, **kw)
+        assert got.dtype == want.dtype and np.array_equal(got, want), kw
+
+
 def test_packed16_kernel_matches_generic_kernel(ib, oracle, monkeypatch):
     """Same plan through both device kernels (INTFFT_DISABLE_FAST16 selects the generic one)."""
     g = ib.Generics(NFFT=12, DATA_WIDTH=16, FORMAT=0)
