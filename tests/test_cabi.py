@@ -143,3 +143,34 @@ def test_describe_rejects_what_does_not_elaborate():
         ib.describe(ib.Generics(NFFT=12, DATA_WIDTH=16, TWDL_WIDTH=30), 1, 0)
     with pytest.raises(ib.IntfftError):
         ib.describe(ib.Generics(NFFT=12, DATA_WIDTH=16, FORMAT=1, RNDMODE=1), 1, 0)
+
+
+def _container_bytes(width):
+    return 4 if width <= 16 else (8 if width <= 32 else 16)        # bytes per complex sample
+
+
+def test_every_plan_covers_each_stage_bit_once_and_chains_its_containers():
+    """Host logic over the whole grid of generics: whatever kernels are chosen, the passes of a plan partition the
+    NFFT stage bits, run them in the direction's order, and hand containers on consistently."""
+    pat = re.compile(r"(\w+)\[bits (\d+)\.\.(\d+), (\d+)->(\d+) B")
+    checked = 0
+    for nfft, dw, tw, fmt, rnd, direction in itertools.product(
+            range(3, 21), (8, 12, 16, 18, 24, 27, 32, 36, 40, 48), (12, 16, 18, 24), (0, 1), (0, 1), (0, 1)):
+        g = ib.Generics(NFFT=nfft, DATA_WIDTH=dw, TWDL_WIDTH=tw, FORMAT=fmt, RNDMODE=rnd)
+        if ib.validate(g, direction) != 0:
+            continue
+        text = ib.describe(g, 4, direction)
+        passes = [(m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4)), int(m.group(5))) for m in pat.finditer(text)]
+        assert passes, text
+        bits = sorted((lo, hi) for _, lo, hi, _, _ in passes)
+        assert bits[0][0] == 0 and bits[-1][1] == nfft - 1, text
+        for (l0, h0), (l1, h1) in zip(bits, bits[1:]):
+            assert l1 == h0 + 1, text
+        order = [lo for _, lo, _, _, _ in passes]
+        assert order == sorted(order, reverse=(direction == 0)), text      # DIF walks the bits downwards
+        assert passes[0][3] == _container_bytes(dw), text
+        assert passes[-1][4] == _container_bytes(dw + fmt * nfft), text
+        for a, b in zip(passes, passes[1:]):
+            assert a[4] == b[3], text
+        checked += 1
+    assert checked > 2000
