@@ -12,8 +12,12 @@
 // both ways).  --top17 dumps only the 17 most significant bits of every output, as that testbench does.
 // --pair runs int_fft_ifft_pair (FFT then IFFT on DATA_WIDTH + FORMAT*NFFT bits) instead of one core.
 //
+// --describe prints what the generics elaborate to (output width, kernel chain) and exits; it needs neither files
+// nor a GPU — the counterpart of reading the synthesis log for the multiplier / buffer variants generated.
+//
 // usage: intfft_host [--ifft | --pair] [--nfft N] [--dw W] [--tw W] [--mode UNSCALED|ROUNDING|TRUNCATE]
 //                    [--xser OLD|NEW] [--no-fly] [--lanes] [--top17] <in.dat> <out.dat>
+//        intfft_host --describe [--ifft] [--nfft N] [--dw W] [--tw W] [--mode ...] [--xser ...]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -60,7 +64,7 @@ int main(int argc, char **argv)
 {
     intfft_generics g{7, 16, 16, 1, 0, 1, 1, 0};   // the testbench defaults: NFFT=7, 16/16, XSERIES="NEW"
     std::string in_path, out_path;
-    bool lanes = false, top17 = false, pair = false;
+    bool lanes = false, top17 = false, pair = false, describe = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&](const char *name) -> const char * {
@@ -69,6 +73,7 @@ int main(int argc, char **argv)
         };
         if (a == "--ifft") g.direction = 1;
         else if (a == "--pair") pair = true;
+        else if (a == "--describe") describe = true;
         else if (a == "--lanes") lanes = true;
         else if (a == "--top17") top17 = true;
         else if (a == "--nfft") g.nfft_log2 = std::atoi(next("--nfft"));
@@ -85,8 +90,17 @@ int main(int argc, char **argv)
         } else if (in_path.empty()) in_path = a;
         else out_path = a;
     }
+    if (describe) {
+        char chain[512];
+        const int sd = intfft_describe(&g, 1, chain, sizeof chain);
+        if (sd) return fail("generics", sd);
+        std::printf("%s NFFT=%d DATA_WIDTH=%d TWDL_WIDTH=%d FORMAT=%d RNDMODE=%d XSER=%s USE_FLY=%d: %d-bit out, %s\n",
+                    g.direction ? "int_ifftNk" : "int_fftNk", g.nfft_log2, g.data_width, g.twdl_width, g.format, g.rndmode,
+                    g.xser ? "NEW" : "OLD", g.use_fly, g.data_width + g.format * g.nfft_log2, chain);
+        return 0;
+    }
     if (in_path.empty() || out_path.empty()) {
-        std::fprintf(stderr, "usage: intfft_host [options] <in.dat> <out.dat>\n");
+        std::fprintf(stderr, "usage: intfft_host [options] <in.dat> <out.dat>   |   intfft_host --describe [options]\n");
         return 2;
     }
     int st = intfft_validate(&g);

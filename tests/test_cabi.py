@@ -174,3 +174,14 @@ def test_every_plan_covers_each_stage_bit_once_and_chains_its_containers():
             assert a[4] == b[3], text
         checked += 1
     assert checked > 2000
+
+
+def test_cpp_host_describes_a_plan_without_a_device():
+    import subprocess
+    exe = os.path.join(ROOT, "intfftk_b200", "intfft_host")
+    if not os.path.exists(exe):
+        pytest.skip("intfft_host not built")
+    out = subprocess.run([exe, "--describe", "--nfft", "20", "--dw", "16", "--mode", "TRUNCATE"], capture_output=True, text=True)
+    assert out.returncode == 0 and "fast16_strided[bits 12..19" in out.stdout and "16-bit out" in out.stdout
+    bad = subprocess.run([exe, "--describe", "--tw", "30"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "elaborate" in bad.stderr
