@@ -86,7 +86,8 @@ int intfft_plan_destroy(intfft_plan *p);
 int intfft_query(const intfft_plan *p, intfft_layout *l);
 
 /* Run `batch` frames. d_in / d_out are DEVICE pointers in the flat layout above; asynchronous on
- * `cuda_stream` (a cudaStream_t, NULL = default stream). d_in == d_out is allowed when the input
+ * `cuda_stream` (a cudaStream_t, NULL = default stream).  Plans with two passes (NFFT >= 13 mostly) run the
+ * batch in groups of frames small enough for the intermediate to stay in the L2 cache between the passes. d_in == d_out is allowed when the input
  * and output containers have the same size. Both pointers must be 16-byte aligned (the kernels move
  * frames with 16-byte vector and TMA bulk accesses; cudaMalloc memory and any whole-frame offset into
  * it qualify), otherwise INTFFT_EINVAL. Replaces driving DI_RE0/IM0/RE1/IM1 + DI_ENA and
@@ -94,8 +95,23 @@ int intfft_query(const intfft_plan *p, intfft_layout *l);
 int intfft_exec(intfft_plan *p, const void *d_in, void *d_out, void *cuda_stream);
 
 /* Same through HOST buffers: H2D copy, exec, D2H copy, synchronised on return.  This is the call a
- * testbench-style host makes (tb/fft_signle_test.vhd:154-358 replays a file through the core). */
+ * testbench-style host makes (tb/fft_signle_test.vhd:154-358 replays a file through the core).
+ * The batch streams through a ring of three ~32 MiB device staging buffers on three streams (copy in /
+ * kernels / copy out), so the device footprint does not depend on the batch; pinned host buffers
+ * (intfft_host_alloc) are needed for the copies to overlap.  On any error every internal stream is
+ * synchronised before returning: no copy touches h_in / h_out afterwards. */
 int intfft_exec_host(intfft_plan *p, const void *h_in, void *h_out);
+
+/* Page-locked host memory, usable from every device of the process (cudaHostAllocPortable). */
+int intfft_host_alloc(void **h_ptr, size_t bytes);
+int intfft_host_free(void *h_ptr);
+
+/* Threading.  A plan is immutable after creation as far as the DEVICE path is concerned: intfft_exec and
+ * intfft_exec_natural copy the per-call state (pointers, frame counts, the natural-order flag) and may be
+ * called concurrently from several host threads on different streams (the caller orders accesses to the
+ * buffers, and to the plan's own intermediate for multi-pass plans and intfft_exec_natural, by using one
+ * stream per plan or events).  The HOST path (intfft_exec_host, intfft_pair_exec_host) owns staging buffers
+ * and streams that are created on first use; those calls are serialised per plan by an internal lock. */
 
 /* Twiddle read-back: the W(k), k = 0 .. 2^stage - 1, that rom_twiddle_int(STAGE = stage) streams
  * (rom_twiddle_int.vhd:98-248); stage >= 2.  Host-only, needs no device. */
@@ -111,6 +127,25 @@ int intfft_pair_create(intfft_pair **out, const intfft_generics *g, int fly_inv,
 int intfft_pair_destroy(intfft_pair *p);
 int intfft_pair_query(const intfft_pair *p, intfft_layout *l);
 int intfft_pair_exec(intfft_pair *p, const void *d_in, void *d_out, void *cuda_stream);
+/* The same through host buffers (what tb/fft_double_test.vhd:154-217 does with di_double.dat -> dout_pair.dat):
+ * the spectrum never leaves the device. */
+int intfft_pair_exec_host(intfft_pair *p, const void *h_in, void *h_out);
+
+/* Multi-GPU: ONE process driving several devices.  Frames are independent (the reference
+ * streams frame after frame through one core, int_fftNk.vhd:15-21), so the batch is cut into contiguous
+ * shards — shard i = frames [batch*i/n, batch*(i+1)/n) on devices[i] — and every device runs the same plan
+ * on its shard; there is no exchange step and no collective.  intfft_multi_exec_host takes ONE host batch
+ * (pinned: intfft_host_alloc) and drives one copy/compute pipeline per device from its own host thread.
+ * intfft_multi_exec runs device-resident shards: d_in[i] / d_out[i] / cuda_streams[i] live on devices[i]
+ * (cuda_streams may be NULL = default streams); asynchronous like intfft_exec. */
+typedef struct intfft_multi intfft_multi;
+int intfft_multi_create(intfft_multi **out, const intfft_generics *g, int64_t batch, const int *devices, int n_devices);
+int intfft_multi_destroy(intfft_multi *m);
+int intfft_multi_devices(const intfft_multi *m);
+int intfft_multi_query(const intfft_multi *m, intfft_layout *l);   /* layout of the WHOLE batch */
+int intfft_multi_shard(const intfft_multi *m, int i, int *device, int64_t *first_frame, int64_t *frames);
+int intfft_multi_exec_host(intfft_multi *m, const void *h_in, void *h_out);
+int intfft_multi_exec(intfft_multi *m, const void *const *d_in, void *const *d_out, void *const *cuda_streams);
 
 /* f1: int_fft_single_path semantics — natural order in AND out
  * (main/int_fft_single_path.vhd:157-268: inbuf_half_path -> int_fftNk -> outbuf_half_path -> int_bitrev_order).

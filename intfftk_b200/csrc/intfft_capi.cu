@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "intfft_internal.h"
@@ -39,6 +40,9 @@ int validate(const intfft_generics *g)
         const int dtw = g->data_width + ii * g->format;
         const int dtwc = g->direction ? dtw : dtw + g->format;
         if (s > 1 && dtwc >= cm.lim_none) return INTFFT_EINVAL;   // no multiplier is generated
+        // trpl18: the product slice dspP_M1(MAW+MBW-2 downto MBW-1) must lie inside the 79 / 77-bit product
+        // (int_cmult_trpl18_dsp48.vhd:151-152); beyond that the entity does not elaborate
+        if (s > 1 && dtwc >= cm.lim_dbl && dtwc + g->twdl_width - 2 > cm.trpl_pwd - 1) return INTFFT_EINVAL;
         if (dtw + 1 > 96) return INTFFT_EINVAL;                  // int_addsub_dsp48.vhd:16-22
     }
     const int worst = g->data_width + g->format * n + ((!g->format && g->rndmode) ? 1 : 0);
@@ -215,13 +219,33 @@ extern "C" {
 
 int intfft_validate(const intfft_generics *g) { return validate(g); }
 
+// frames * 2^n complex samples must stay below 2^40 (checked without shifting the caller's value)
+static bool batch_ok(int64_t batch, int nfft_log2) { return batch >= 1 && batch <= ((1ll << 40) >> nfft_log2); }
+
+// Group size of a two-pass plan (see Plan::group_frames).  INTFFT_GROUP_MB overrides the budget (0 = no groups).
+static long long pick_group_frames(const Plan &pl)
+{
+    if (pl.passes.size() != 2) return 0;
+    long long mb = 24;
+    if (const char *e = std::getenv("INTFFT_GROUP_MB")) mb = std::atoll(e);
+    if (mb <= 0) return 0;
+    const PassParams &a = pl.passes[0].kp, &b = pl.passes[1].kp;
+    // bytes per frame that should survive in L2 between the passes: what the first pass writes, plus the
+    // streaming traffic that competes with it (its own input)
+    const long long n = 1ll << pl.g.nfft_log2;
+    const long long per_frame = n * 2 * (a.out_sb + a.in_sb);
+    (void)b;
+    long long gf = (mb << 20) / per_frame;
+    return gf < 1 ? 1 : gf;
+}
+
 int intfft_plan_create(intfft_plan **out, const intfft_generics *g, int64_t batch, int device)
 {
     if (!out) return INTFFT_EINVAL;
     *out = nullptr;
     int st = validate(g);
     if (st) return st;
-    if (batch < 1 || (batch << g->nfft_log2) > (1ll << 40)) return INTFFT_EINVAL;
+    if (!batch_ok(batch, g->nfft_log2)) return INTFFT_EINVAL;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return INTFFT_ECUDA;
     DeviceGuard guard(device);
@@ -239,6 +263,11 @@ int intfft_plan_create(intfft_plan **out, const intfft_generics *g, int64_t batc
     pl->out_sb = scalar_bytes(pl->out_width);
     cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, device);
     build_passes(*pl);
+    pl->group_frames = pick_group_frames(*pl);
+    if (pl->group_frames && pl->scratch_bytes[0]) {        // the intermediate only ever holds one group
+        const long long gf = pl->group_frames < batch ? pl->group_frames : batch;
+        pl->scratch_bytes[0] = (size_t)(gf << g->nfft_log2) * 2 * pl->passes[0].kp.out_sb;
+    }
     st = upload_twiddles(*pl);
     if (st == INTFFT_OK && pl->scratch_bytes[0]) {
         if (cudaMalloc(&pl->scratch[0], pl->scratch_bytes[0]) != cudaSuccess) st = INTFFT_ENOMEM;
@@ -246,6 +275,20 @@ int intfft_plan_create(intfft_plan **out, const intfft_generics *g, int64_t batc
     if (st != INTFFT_OK) { intfft_plan_destroy(pl); return st; }
     *out = pl;
     return INTFFT_OK;
+}
+
+static void pipe_destroy(HostPipe &hp)
+{
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+        cudaFree(hp.d_in[i]);
+        cudaFree(hp.d_out[i]);
+        if (hp.ev_in[i]) cudaEventDestroy((cudaEvent_t)hp.ev_in[i]);
+        if (hp.ev_k[i]) cudaEventDestroy((cudaEvent_t)hp.ev_k[i]);
+        if (hp.ev_out[i]) cudaEventDestroy((cudaEvent_t)hp.ev_out[i]);
+    }
+    if (hp.s_in) cudaStreamDestroy((cudaStream_t)hp.s_in);
+    if (hp.s_k) cudaStreamDestroy((cudaStream_t)hp.s_k);
+    if (hp.s_out) cudaStreamDestroy((cudaStream_t)hp.s_out);
 }
 
 int intfft_plan_destroy(intfft_plan *p)
@@ -256,12 +299,8 @@ int intfft_plan_destroy(intfft_plan *p)
     cudaFree(p->d_twp);
     cudaFree(p->scratch[0]);
     cudaFree(p->scratch[1]);
-    cudaFree(p->h2d);
-    cudaFree(p->d2h);
     cudaFree(p->nat);
-    for (void *e : p->ev_in) cudaEventDestroy((cudaEvent_t)e);
-    for (void *e : p->ev_k) cudaEventDestroy((cudaEvent_t)e);
-    if (p->s_in) { cudaStreamDestroy((cudaStream_t)p->s_in); cudaStreamDestroy((cudaStream_t)p->s_k); cudaStreamDestroy((cudaStream_t)p->s_out); }
+    pipe_destroy(p->pipe);
     delete p;
     return INTFFT_OK;
 }
@@ -284,37 +323,67 @@ int intfft_query(const intfft_plan *p, intfft_layout *l)
     return INTFFT_OK;
 }
 
-// run `frames` frames (<= plan batch) starting at d_in / d_out
-static int exec_frames(intfft_plan *p, const void *d_in, void *d_out, long long frames, void *cuda_stream)
+// One pass over `frames` frames.  The plan's descriptor is COPIED and the per-call fields are set on the copy:
+// nothing in the plan changes at exec time, so one plan can be driven from several host threads / streams.
+static int run_pass(const intfft_plan *p, size_t i, const void *in, void *out, long long frames, int natural,
+                    void *cuda_stream)
 {
     const int n = p->g.nfft_log2;
-    const long long total = frames << n;
+    const bool dit = p->g.direction != 0;
+    PassDesc pd = p->passes[i];
+    pd.kp.in = in;
+    pd.kp.out = out;
+    pd.kp.tw = p->d_tw;
+    pd.kp.total = frames << n;
+    pd.kp.n_tiles = pd.kp.c > 0 ? (frames << (n - pd.kp.L)) : ((pd.kp.total + (1ll << pd.kp.L) - 1) >> pd.kp.L);
+    pd.natural = natural;
+    int e;
+    if (pd.path == 1)
+        e = pd.kp.c > 0 ? launch_fast16_strided(pd, p->mode, dit, p->d_twp, p->num_sms, cuda_stream)
+                        : launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream);
+    else if (pd.path == 2)
+        e = launch_fast32(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
+    else if (pd.path == 3)
+        e = launch_fast64(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
+    else if (pd.path == 4)
+        e = launch_fast64_strided(pd, p->mode, dit, p->d_tw, p->num_sms, cuda_stream);
+    else
+        e = launch_tile_pass(pd, p->mode, dit, p->num_sms, cuda_stream);
+    return e ? INTFFT_ECUDA : INTFFT_OK;
+}
+
+// run `frames` frames (<= plan batch) starting at d_in / d_out
+static int exec_frames(const intfft_plan *p, const void *d_in, void *d_out, long long frames, void *cuda_stream,
+                       int natural = 0)
+{
+    const int n = p->g.nfft_log2;
     if (!p->g.use_fly) {
-        const int e = launch_bypass(d_in, d_out, total * 2, p->in_sb, p->out_sb, p->g.data_width,
+        const int e = launch_bypass(d_in, d_out, (frames << n) * 2, p->in_sb, p->out_sb, p->g.data_width,
                                     p->g.format, cuda_stream);
         return e ? INTFFT_ECUDA : INTFFT_OK;
     }
-    const bool dit = p->g.direction != 0;
-    for (size_t i = 0; i < p->passes.size(); ++i) {
-        PassDesc &pd = p->passes[i];
-        pd.kp.in = (i == 0) ? d_in : (pd.scratch_in >= 0 ? p->scratch[pd.scratch_in] : d_out);
-        pd.kp.out = (i + 1 == p->passes.size()) ? d_out : (pd.scratch_out >= 0 ? p->scratch[pd.scratch_out] : d_out);
-        pd.kp.tw = p->d_tw;
-        pd.kp.total = total;
-        pd.kp.n_tiles = pd.kp.c > 0 ? (frames << (n - pd.kp.L)) : ((total + (1ll << pd.kp.L) - 1) >> pd.kp.L);
-        int e;
-        if (pd.path == 1)
-            e = pd.kp.c > 0 ? launch_fast16_strided(pd, p->mode, dit, p->d_twp, p->num_sms, cuda_stream)
-                            : launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream);
-        else if (pd.path == 2)
-            e = launch_fast32(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
-        else if (pd.path == 3)
-            e = launch_fast64(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
-        else if (pd.path == 4)
-            e = launch_fast64_strided(pd, p->mode, dit, p->d_tw, p->num_sms, cuda_stream);
-        else
-            e = launch_tile_pass(pd, p->mode, dit, p->num_sms, cuda_stream);
-        if (e) return INTFFT_ECUDA;
+    const size_t np = p->passes.size();
+    if (np == 1) return run_pass(p, 0, d_in, d_out, frames, natural, cuda_stream);
+    const long long in_frame = (1ll << n) * 2 * p->in_sb, out_frame = (1ll << n) * 2 * p->out_sb;
+    const long long gf = (np == 2 && p->group_frames > 0) ? p->group_frames : frames;
+    for (long long f0 = 0; f0 < frames; f0 += gf) {
+        const long long nf = f0 + gf <= frames ? gf : frames - f0;
+        const char *gin = (const char *)d_in + f0 * in_frame;
+        char *gout = (char *)d_out + f0 * out_frame;
+        for (size_t i = 0; i < np; ++i) {
+            const PassDesc &pd = p->passes[i];
+            // intermediates: the plan's scratch (whole batch without groups, else one group, reused) or in place
+            // in the caller's output buffer
+            const long long so = (np == 2 && p->group_frames > 0) ? 0 : f0;
+            const void *in = (i == 0) ? (const void *)gin
+                                      : (pd.scratch_in >= 0 ? (const void *)((char *)p->scratch[pd.scratch_in] + so * (1ll << n) * 2 * pd.kp.in_sb)
+                                                            : (const void *)gout);
+            void *out = (i + 1 == np) ? (void *)gout
+                                      : (pd.scratch_out >= 0 ? (void *)((char *)p->scratch[pd.scratch_out] + so * (1ll << n) * 2 * pd.kp.out_sb)
+                                                             : (void *)gout);
+            const int st = run_pass(p, i, in, out, nf, 0, cuda_stream);
+            if (st) return st;
+        }
     }
     return INTFFT_OK;
 }
@@ -341,14 +410,16 @@ int intfft_exec_natural(intfft_plan *p, const void *d_in, void *d_out, void *cud
     // the reorder acts on the bit-reversed side: the FFT's output / the IFFT's input
     const int n = p->g.nfft_log2;
     // a 4096-point packed-16 FFT reorders inside its own kernel (natural-order stores): no second pass
-    if (!dit && p->g.use_fly && p->passes.size() == 1 && p->passes[0].path == 1 && p->passes[0].kp.g == 12) {
-        p->passes[0].natural = 1;
-        const int st = exec_frames(p, d_in, d_out, p->batch, cuda_stream);
-        p->passes[0].natural = 0;
-        return st;
+    if (!dit && p->g.use_fly && p->passes.size() == 1 && p->passes[0].path == 1 && p->passes[0].kp.g == 12)
+        return exec_frames(p, d_in, d_out, p->batch, cuda_stream, /*natural=*/1);
+    {   // the intermediate is allocated once, under the plan's lock; afterwards it is only read here
+        std::lock_guard<std::mutex> lk(p->pipe.mu);
+        const size_t need = (size_t)(dit ? l.in_bytes : l.out_bytes);
+        if (!p->nat) {
+            if (cudaMalloc(&p->nat, need) != cudaSuccess) return INTFFT_ENOMEM;
+            p->nat_bytes = need;
+        }
     }
-    const size_t need = (size_t)(dit ? l.in_bytes : l.out_bytes);
-    if (!p->nat && cudaMalloc(&p->nat, need) != cudaSuccess) return INTFFT_ENOMEM;
     if (!dit) {
         const int st = exec_frames(p, d_in, p->nat, p->batch, cuda_stream);
         if (st) return st;
@@ -358,60 +429,101 @@ int intfft_exec_natural(intfft_plan *p, const void *d_in, void *d_out, void *cud
     return exec_frames(p, p->nat, d_out, p->batch, cuda_stream);
 }
 
-// Host buffers: the batch is cut into chunks that flow through three streams (H2D copy, kernels,
-// D2H copy), so the two PCIe directions and the SMs work at the same time.
+// ---- host-buffer pipeline -------------------------------------------------------------------------
+// The batch is cut into chunks of ~32 MiB that flow through a ring of kSlots device staging buffers and three
+// streams (H2D copy, kernels, D2H copy): the two PCIe directions and the SMs work at the same time, and the
+// device footprint is kSlots chunks, not the batch (so a batch larger than HBM streams through as well).
+}  // extern "C" (templates cannot have C linkage)
+template <typename Exec>
+static int host_pipeline(HostPipe &hp, long long frames, long long in_per_frame, long long out_per_frame,
+                         const void *h_in, void *h_out, Exec &&exec_chunk)
+{
+    std::lock_guard<std::mutex> lk(hp.mu);
+    if (!hp.s_in) {
+        long long chunk = (32ll << 20) / in_per_frame;
+        if (const char *e = std::getenv("INTFFT_CHUNK_MB")) chunk = ((long long)std::atoll(e) << 20) / in_per_frame;
+        if (chunk < 1) chunk = 1;
+        if (chunk > frames) chunk = frames;
+        hp.chunk_frames = chunk;
+        cudaStream_t a = nullptr, b = nullptr, c = nullptr;
+        if (cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c, cudaStreamNonBlocking) != cudaSuccess)
+            return INTFFT_ECUDA;
+        hp.s_in = a; hp.s_k = b; hp.s_out = c;
+        for (int i = 0; i < HostPipe::kSlots; ++i) {
+            cudaEvent_t e1, e2, e3;
+            if (cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e3, cudaEventDisableTiming) != cudaSuccess)
+                return INTFFT_ECUDA;
+            hp.ev_in[i] = e1; hp.ev_k[i] = e2; hp.ev_out[i] = e3;
+            if (cudaMalloc(&hp.d_in[i], (size_t)(chunk * in_per_frame)) != cudaSuccess ||
+                cudaMalloc(&hp.d_out[i], (size_t)(chunk * out_per_frame)) != cudaSuccess)
+                return INTFFT_ENOMEM;
+        }
+    }
+    cudaStream_t s_in = (cudaStream_t)hp.s_in, s_k = (cudaStream_t)hp.s_k, s_out = (cudaStream_t)hp.s_out;
+    const long long chunk = hp.chunk_frames;
+    int rc = INTFFT_OK;
+    long long c = 0;
+    for (long long f0 = 0; f0 < frames && rc == INTFFT_OK; f0 += chunk, ++c) {
+        const long long nf = f0 + chunk <= frames ? chunk : frames - f0;
+        const int slot = (int)(c % HostPipe::kSlots);
+        // the slot is free once the result of the chunk that used it last has left for the host
+        if (c >= HostPipe::kSlots && cudaStreamWaitEvent(s_in, (cudaEvent_t)hp.ev_out[slot], 0) != cudaSuccess) { rc = INTFFT_ECUDA; break; }
+        if (cudaMemcpyAsync(hp.d_in[slot], (const char *)h_in + f0 * in_per_frame, (size_t)(nf * in_per_frame),
+                            cudaMemcpyHostToDevice, s_in) != cudaSuccess ||
+            cudaEventRecord((cudaEvent_t)hp.ev_in[slot], s_in) != cudaSuccess ||
+            cudaStreamWaitEvent(s_k, (cudaEvent_t)hp.ev_in[slot], 0) != cudaSuccess) { rc = INTFFT_ECUDA; break; }
+        rc = exec_chunk(hp.d_in[slot], hp.d_out[slot], nf, (void *)s_k);
+        if (rc) break;
+        if (cudaEventRecord((cudaEvent_t)hp.ev_k[slot], s_k) != cudaSuccess ||
+            cudaStreamWaitEvent(s_out, (cudaEvent_t)hp.ev_k[slot], 0) != cudaSuccess ||
+            cudaMemcpyAsync((char *)h_out + f0 * out_per_frame, hp.d_out[slot], (size_t)(nf * out_per_frame),
+                            cudaMemcpyDeviceToHost, s_out) != cudaSuccess ||
+            cudaEventRecord((cudaEvent_t)hp.ev_out[slot], s_out) != cudaSuccess) { rc = INTFFT_ECUDA; break; }
+    }
+    // success or not, no copy may still be touching the caller's buffers when this returns
+    const cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_k), e3 = cudaStreamSynchronize(s_out);
+    if (rc == INTFFT_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) rc = INTFFT_ECUDA;
+    if (rc == INTFFT_OK && cudaGetLastError() != cudaSuccess) rc = INTFFT_ECUDA;
+    return rc;
+}
+extern "C" {
+
 int intfft_exec_host(intfft_plan *p, const void *h_in, void *h_out)
 {
     if (!p || !h_in || !h_out) return INTFFT_EINVAL;
     DeviceGuard guard(p->device);
     if (!guard.ok) return INTFFT_ECUDA;
-    intfft_layout l;
-    intfft_query(p, &l);
-    if (!p->h2d && cudaMalloc(&p->h2d, (size_t)l.in_bytes) != cudaSuccess) return INTFFT_ENOMEM;
-    if (!p->d2h && cudaMalloc(&p->d2h, (size_t)l.out_bytes) != cudaSuccess) return INTFFT_ENOMEM;
-    const long long in_per_frame = l.in_bytes / p->batch, out_per_frame = l.out_bytes / p->batch;
-    long long chunk = (32ll << 20) / in_per_frame;          // ~32 MiB of input per chunk
-    if (chunk < 1) chunk = 1;
-    const long long n_chunks = (p->batch + chunk - 1) / chunk;
-    if (!p->s_in) {
-        cudaStream_t a, b, c;
-        if (cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&c, cudaStreamNonBlocking) != cudaSuccess)
-            return INTFFT_ECUDA;
-        p->s_in = a; p->s_k = b; p->s_out = c;
-    }
-    while ((long long)p->ev_in.size() < n_chunks) {
-        cudaEvent_t e1, e2;
-        if (cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess)
-            return INTFFT_ECUDA;
-        p->ev_in.push_back(e1);
-        p->ev_k.push_back(e2);
-    }
-    cudaStream_t s_in = (cudaStream_t)p->s_in, s_k = (cudaStream_t)p->s_k, s_out = (cudaStream_t)p->s_out;
-    for (long long c = 0; c < n_chunks; ++c) {
-        const long long f0 = c * chunk, nf = (f0 + chunk <= p->batch) ? chunk : p->batch - f0;
-        char *di = (char *)p->h2d + f0 * in_per_frame, *dout = (char *)p->d2h + f0 * out_per_frame;
-        if (cudaMemcpyAsync(di, (const char *)h_in + f0 * in_per_frame, (size_t)(nf * in_per_frame),
-                            cudaMemcpyHostToDevice, s_in) != cudaSuccess) return INTFFT_ECUDA;
-        cudaEventRecord((cudaEvent_t)p->ev_in[c], s_in);
-        cudaStreamWaitEvent(s_k, (cudaEvent_t)p->ev_in[c], 0);
-        const int st = exec_frames(p, di, dout, nf, s_k);
-        if (st) return st;
-        cudaEventRecord((cudaEvent_t)p->ev_k[c], s_k);
-        cudaStreamWaitEvent(s_out, (cudaEvent_t)p->ev_k[c], 0);
-        if (cudaMemcpyAsync((char *)h_out + f0 * out_per_frame, dout, (size_t)(nf * out_per_frame),
-                            cudaMemcpyDeviceToHost, s_out) != cudaSuccess) return INTFFT_ECUDA;
-    }
-    if (cudaStreamSynchronize(s_out) != cudaSuccess) return INTFFT_ECUDA;
-    return cudaGetLastError() == cudaSuccess ? INTFFT_OK : INTFFT_ECUDA;
+    const long long n = 1ll << p->g.nfft_log2;
+    return host_pipeline(p->pipe, p->batch, n * 2 * p->in_sb, n * 2 * p->out_sb, h_in, h_out,
+                         [p](const void *di, void *dout, long long nf, void *st) { return exec_frames(p, di, dout, nf, st); });
+}
+
+int intfft_host_alloc(void **h_ptr, size_t bytes)
+{
+    if (!h_ptr || bytes == 0) return INTFFT_EINVAL;
+    *h_ptr = nullptr;
+    // portable: page-locked for every device of the process (intfft_multi_* copies from several devices at once)
+    const cudaError_t e = cudaHostAlloc(h_ptr, bytes, cudaHostAllocPortable);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return INTFFT_ENOMEM; }
+    return e == cudaSuccess ? INTFFT_OK : INTFFT_ECUDA;
+}
+
+int intfft_host_free(void *h_ptr)
+{
+    if (!h_ptr) return INTFFT_EINVAL;
+    return cudaFreeHost(h_ptr) == cudaSuccess ? INTFFT_OK : INTFFT_ECUDA;
 }
 
 // ---- f2: int_fft_ifft_pair ----------------------------------------------------------------------
 struct intfft_pair {
     intfft_plan *fwd = nullptr, *inv = nullptr;
     void *mid = nullptr;           // spectrum between the two cores (bit-reversed order), device
+    long long mid_frames = 0;      // frames `mid` holds: the pair runs group by group so the spectrum stays in L2
+    HostPipe pipe;
 };
 
 int intfft_pair_create(intfft_pair **out, const intfft_generics *g, int fly_inv, int64_t batch, int device)
@@ -432,9 +544,15 @@ int intfft_pair_create(intfft_pair **out, const intfft_generics *g, int fly_inv,
     if (!st) st = intfft_plan_create(&p->inv, &gi, batch, device);
     if (!st) {
         DeviceGuard guard(device);
-        intfft_layout l;
-        intfft_query(p->fwd, &l);
-        if (cudaMalloc(&p->mid, (size_t)l.out_bytes) != cudaSuccess) st = INTFFT_ENOMEM;
+        // the spectrum of one group of frames: small enough to be read back from L2 by the inverse core
+        const long long frame_bytes = (1ll << g->nfft_log2) * 2 * p->fwd->out_sb;
+        long long mb = 32;
+        if (const char *e = std::getenv("INTFFT_PAIR_GROUP_MB")) mb = std::atoll(e);
+        long long gfm = mb > 0 ? (mb << 20) / frame_bytes : batch;
+        if (gfm < 1) gfm = 1;
+        if (gfm > batch) gfm = batch;
+        p->mid_frames = gfm;
+        if (cudaMalloc(&p->mid, (size_t)(gfm * frame_bytes)) != cudaSuccess) st = INTFFT_ENOMEM;
     }
     if (st) { intfft_pair_destroy(p); return st; }
     *out = p;
@@ -444,7 +562,11 @@ int intfft_pair_create(intfft_pair **out, const intfft_generics *g, int fly_inv,
 int intfft_pair_destroy(intfft_pair *p)
 {
     if (!p) return INTFFT_EINVAL;
-    if (p->mid && p->fwd) { DeviceGuard guard(p->fwd->device); cudaFree(p->mid); }
+    if (p->fwd) {
+        DeviceGuard guard(p->fwd->device);
+        cudaFree(p->mid);
+        pipe_destroy(p->pipe);
+    }
     if (p->fwd) intfft_plan_destroy(p->fwd);
     if (p->inv) intfft_plan_destroy(p->inv);
     delete p;
@@ -466,11 +588,127 @@ int intfft_pair_query(const intfft_pair *p, intfft_layout *l)
     return INTFFT_OK;
 }
 
+static int pair_frames(const intfft_pair *p, const void *d_in, void *d_out, long long frames, void *cuda_stream)
+{
+    const long long n = 1ll << p->fwd->g.nfft_log2;
+    const long long in_frame = n * 2 * p->fwd->in_sb, out_frame = n * 2 * p->inv->out_sb;
+    for (long long f0 = 0; f0 < frames; f0 += p->mid_frames) {
+        const long long nf = f0 + p->mid_frames <= frames ? p->mid_frames : frames - f0;
+        int st = exec_frames(p->fwd, (const char *)d_in + f0 * in_frame, p->mid, nf, cuda_stream);
+        if (!st) st = exec_frames(p->inv, p->mid, (char *)d_out + f0 * out_frame, nf, cuda_stream);
+        if (st) return st;
+    }
+    return INTFFT_OK;
+}
+
 int intfft_pair_exec(intfft_pair *p, const void *d_in, void *d_out, void *cuda_stream)
 {
     if (!p || !d_in || !d_out) return INTFFT_EINVAL;
-    const int st = intfft_exec(p->fwd, d_in, p->mid, cuda_stream);
-    return st ? st : intfft_exec(p->inv, p->mid, d_out, cuda_stream);
+    if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15u) return INTFFT_EINVAL;
+    DeviceGuard guard(p->fwd->device);
+    if (!guard.ok) return INTFFT_ECUDA;
+    return pair_frames(p, d_in, d_out, p->fwd->batch, cuda_stream);
+}
+
+int intfft_pair_exec_host(intfft_pair *p, const void *h_in, void *h_out)
+{
+    if (!p || !h_in || !h_out) return INTFFT_EINVAL;
+    DeviceGuard guard(p->fwd->device);
+    if (!guard.ok) return INTFFT_ECUDA;
+    const long long n = 1ll << p->fwd->g.nfft_log2;
+    return host_pipeline(p->pipe, p->fwd->batch, n * 2 * p->fwd->in_sb, n * 2 * p->inv->out_sb, h_in, h_out,
+                         [p](const void *di, void *dout, long long nf, void *st) { return pair_frames(p, di, dout, nf, st); });
+}
+
+// ---- multi-GPU: one process, several devices ---------------------------------------
+// Frames are independent, so the batch is cut into contiguous shards, one per device, and every device runs
+// the same plan on its shard: no exchange step, no collective.  The host path drives one pipeline per device
+// from its own host thread.
+struct intfft_multi {
+    std::vector<intfft_plan *> plans;
+    std::vector<long long> first;      // first frame of each shard
+    long long batch = 0;
+    intfft_generics g{};
+};
+
+int intfft_multi_create(intfft_multi **out, const intfft_generics *g, int64_t batch, const int *devices, int n_devices)
+{
+    if (!out) return INTFFT_EINVAL;
+    *out = nullptr;
+    int st = validate(g);
+    if (st) return st;
+    if (!devices || n_devices < 1 || n_devices > 64 || !batch_ok(batch, g->nfft_log2) || batch < n_devices) return INTFFT_EINVAL;
+    intfft_multi *m = new (std::nothrow) intfft_multi();
+    if (!m) return INTFFT_ENOMEM;
+    m->batch = batch;
+    m->g = *g;
+    for (int i = 0; i < n_devices && st == INTFFT_OK; ++i) {
+        // same split as intfftk_b200/sharding.py: shards differ by at most one frame and tile the batch
+        const long long lo = batch * i / n_devices, hi = batch * (i + 1) / n_devices;
+        intfft_plan *pl = nullptr;
+        st = intfft_plan_create(&pl, g, hi - lo, devices[i]);
+        if (st == INTFFT_OK) { m->plans.push_back(pl); m->first.push_back(lo); }
+    }
+    if (st) { intfft_multi_destroy(m); return st; }
+    *out = m;
+    return INTFFT_OK;
+}
+
+int intfft_multi_destroy(intfft_multi *m)
+{
+    if (!m) return INTFFT_EINVAL;
+    for (intfft_plan *p : m->plans) intfft_plan_destroy(p);
+    delete m;
+    return INTFFT_OK;
+}
+
+int intfft_multi_query(const intfft_multi *m, intfft_layout *l)
+{
+    if (!m || !l || m->plans.empty()) return INTFFT_EINVAL;
+    intfft_query(m->plans[0], l);
+    l->batch = m->batch;
+    l->in_bytes = m->batch * l->n * 2 * l->in_scalar_bytes;
+    l->out_bytes = m->batch * l->n * 2 * l->out_scalar_bytes;
+    return INTFFT_OK;
+}
+
+int intfft_multi_shard(const intfft_multi *m, int i, int *device, int64_t *first_frame, int64_t *frames)
+{
+    if (!m || i < 0 || i >= (int)m->plans.size()) return INTFFT_EINVAL;
+    if (device) *device = m->plans[i]->device;
+    if (first_frame) *first_frame = m->first[i];
+    if (frames) *frames = m->plans[i]->batch;
+    return INTFFT_OK;
+}
+
+int intfft_multi_devices(const intfft_multi *m) { return m ? (int)m->plans.size() : INTFFT_EINVAL; }
+
+int intfft_multi_exec_host(intfft_multi *m, const void *h_in, void *h_out)
+{
+    if (!m || !h_in || !h_out) return INTFFT_EINVAL;
+    const long long n = 1ll << m->g.nfft_log2;
+    const size_t nd = m->plans.size();
+    std::vector<int> rc(nd, INTFFT_OK);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < nd; ++i) {
+        intfft_plan *p = m->plans[i];
+        const char *hi = (const char *)h_in + m->first[i] * n * 2 * p->in_sb;
+        char *ho = (char *)h_out + m->first[i] * n * 2 * p->out_sb;
+        th.emplace_back([p, hi, ho, &rc, i] { rc[i] = intfft_exec_host(p, hi, ho); });
+    }
+    for (std::thread &t : th) t.join();
+    for (int r : rc) if (r) return r;
+    return INTFFT_OK;
+}
+
+int intfft_multi_exec(intfft_multi *m, const void *const *d_in, void *const *d_out, void *const *cuda_streams)
+{
+    if (!m || !d_in || !d_out) return INTFFT_EINVAL;
+    for (size_t i = 0; i < m->plans.size(); ++i) {
+        const int st = intfft_exec(m->plans[i], d_in[i], d_out[i], cuda_streams ? cuda_streams[i] : nullptr);
+        if (st) return st;
+    }
+    return INTFFT_OK;
 }
 
 int intfft_twiddles(const intfft_generics *g, int stage, int32_t *h_re, int32_t *h_im)
@@ -518,9 +756,10 @@ int intfft_checksum(const void *d_buf, int64_t n_scalars, int sb, uint64_t *h_su
 
 int intfft_describe(const intfft_generics *g, int64_t batch, char *buf, size_t len)
 {
-    if (!g || !buf || len == 0 || batch < 1) return INTFFT_EINVAL;
+    if (!g || !buf || len == 0) return INTFFT_EINVAL;
     const int st = validate(g);
     if (st) return st;
+    if (!batch_ok(batch, g->nfft_log2)) return INTFFT_EINVAL;
     Plan pl;                                   // host-side description only: nothing is allocated on a device
     pl.g = *g;
     pl.batch = batch;

@@ -2,6 +2,7 @@
 // Nothing here crosses the C-ABI (include/intfft.h).
 #pragma once
 #include <cstdint>
+#include <mutex>
 #include <vector>
 
 #include <vector_types.h>
@@ -18,6 +19,9 @@ namespace intfft {
 struct CmultConsts {
     int lim_single, lim_dbl, lim_none;
     int sh_single, k_pre, sh_post;
+    int trpl_awd;     // triple arrangement: the wide multiplier's data port is this many bits (61 / 59 for trpl18:
+                      // dspA_M1 <= SXT(M1_AA, AWD), int_cmult_trpl18_dsp48.vhd:161-162); wider data is cut there
+    int trpl_pwd;     // and its product has this many bits (79 / 77): DTW + TWD - 2 must stay below it (:151)
 };
 CmultConsts cmult_consts(int twdl_width, int xser);
 
@@ -58,7 +62,22 @@ struct PassDesc {
     int scratch_in, scratch_out;  // -1 = user buffer, else index of plan scratch buffer
     int path;              // 0 generic tile kernel, 1 packed-16 kernels, 2 32-bit-lane kernels, 3 64-bit-lane low-8 kernel,
                            // 4 64-bit-lane strided kernel
-    int natural = 0;       // exec time: this (single, 4096-point packed-16 DIF) pass also applies int_bitrev_order
+    int natural = 0;       // exec time (set on a per-call COPY of the descriptor, never on the plan's): this single
+                           // 4096-point packed-16 DIF pass also applies int_bitrev_order
+};
+
+// Host-buffer pipeline state (intfft_exec_host and friends): a ring of chunk-sized device staging buffers and
+// three streams (H2D copies / kernels / D2H copies).  Created on first use, guarded by `mu`: host-path calls on
+// one plan are serialised, device-path calls (intfft_exec) never touch it.
+struct HostPipe {
+    static constexpr int kSlots = 3;
+    std::mutex mu;
+    void *d_in[kSlots] = {nullptr, nullptr, nullptr}, *d_out[kSlots] = {nullptr, nullptr, nullptr};
+    long long chunk_frames = 0;
+    void *s_in = nullptr, *s_k = nullptr, *s_out = nullptr;   // cudaStream_t
+    void *ev_in[kSlots] = {nullptr, nullptr, nullptr};        // cudaEvent_t: chunk landed in its slot
+    void *ev_k[kSlots] = {nullptr, nullptr, nullptr};         //              kernels of the slot's chunk done
+    void *ev_out[kSlots] = {nullptr, nullptr, nullptr};       //              slot's result copied back (slot free)
 };
 
 struct Plan {
@@ -74,10 +93,14 @@ struct Plan {
     int lw32_r[16] = {0}, lw32_i[16] = {0};  // same, not pre-shifted (32-bit-lane kernels)
     void *scratch[2] = {nullptr, nullptr};
     size_t scratch_bytes[2] = {0, 0};
-    void *h2d = nullptr, *d2h = nullptr;  // device staging for intfft_exec_host
-    void *nat = nullptr;                  // bit-reversed intermediate of intfft_exec_natural
-    void *s_in = nullptr, *s_k = nullptr, *s_out = nullptr;   // cudaStream_t: H2D / kernels / D2H pipeline
-    std::vector<void *> ev_in, ev_k;                          // cudaEvent_t per chunk
+    // Two-pass plans run group by group: `group_frames` frames go through BOTH passes before the next group
+    // starts, so what the first pass wrote is still in the 126 MB L2 when the second pass reads it (and, for
+    // in-place intermediates, is overwritten there before it is ever written back): HBM sees the algorithmic
+    // bytes once.  0 = whole batch at once.
+    long long group_frames = 0;
+    void *nat = nullptr;                  // bit-reversed intermediate of intfft_exec_natural (allocated at creation
+    size_t nat_bytes = 0;                 // time when the plan needs one, so exec never mutates the plan)
+    HostPipe pipe;
     int num_sms = 0;
 };
 

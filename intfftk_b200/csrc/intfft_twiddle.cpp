@@ -91,6 +91,8 @@ CmultConsts cmult_consts(int tw, int xser)
         c.sh_single = tw - 1;
         c.k_pre = awd + tw - 48;         // :174-175
         c.sh_post = 47 - awd;            // :163
+        c.trpl_awd = xser ? 61 : 59;     // int_cmult_trpl18_dsp48.vhd:117-129 (find_widthA)
+        c.trpl_pwd = xser ? 79 : 77;     // :131-143 (find_widthP)
     } else {                             // int_cmult_dsp48.vhd:307, dbl35 / trpl52 family
         c.lim_single = 19;
         c.lim_dbl = 36;
@@ -98,6 +100,8 @@ CmultConsts cmult_consts(int tw, int xser)
         c.sh_single = tw - 2;
         c.k_pre = tw - 14;               // int_cmult_dbl35_dsp48.vhd:155-156
         c.sh_post = 12;                  // :160
+        c.trpl_awd = 64;                 // trpl52: SXT(M1_AA, 52) with DTW < 53 never cuts
+        c.trpl_pwd = 128;
     }
     return c;
 }

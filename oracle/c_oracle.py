@@ -36,6 +36,8 @@ def lib() -> ctypes.CDLL:
         L.orc_twiddle.argtypes = [P(OrcGenerics), ctypes.c_int, ctypes.c_int64,
                                   P(ctypes.c_int64), P(ctypes.c_int64)]
         L.orc_twiddle_table.argtypes = [P(OrcGenerics), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_cmult.argtypes = [ctypes.c_int] * 3 + [ctypes.c_int64] * 4 + [P(ctypes.c_int64)] * 2
+        L.orc_fly.argtypes = [P(OrcGenerics), ctypes.c_int, ctypes.c_int, ctypes.c_int64, P(ctypes.c_int64)]
         L.orc_transform.argtypes = [P(OrcGenerics)] + [ctypes.c_void_p] * 4
         L.orc_batch.argtypes = [P(OrcGenerics), ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.orc_fill_random.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_uint64]
@@ -69,6 +71,22 @@ def twiddle_table(g: OrcGenerics, stage: int):
     if st:
         raise ValueError(f"orc_twiddle_table status {st}")
     return re, im
+
+
+def cmult(dtw: int, twd: int, xser_new: int, d_re: int, d_im: int, w_re: int, w_im: int):
+    """int_cmult_dsp48(DTW, TWD, XSER) on one operand pair (two's-complement values in, values out)."""
+    o_re, o_im = ctypes.c_int64(), ctypes.c_int64()
+    st = lib().orc_cmult(dtw, twd, xser_new, d_re, d_im, w_re, w_im, ctypes.byref(o_re), ctypes.byref(o_im))
+    if st:
+        raise ValueError(f"orc_cmult status {st}")
+    return o_re.value, o_im.value
+
+
+def fly(g: OrcGenerics, stage: int, dtw: int, k: int, a_re: int, a_im: int, b_re: int, b_im: int):
+    """One butterfly of STAGE `stage` at input width dtw, beat k (twiddle generated inside)."""
+    ab = (ctypes.c_int64 * 4)(a_re, a_im, b_re, b_im)
+    lib().orc_fly(ctypes.byref(g), stage, dtw, k, ab)
+    return tuple(int(v) for v in ab)
 
 
 def transform(g: OrcGenerics, re, im):

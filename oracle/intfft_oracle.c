@@ -57,7 +57,9 @@ static int cmult_variant(int dtw, int twd, int xser_new)
     if (twd < 19) {                                   /* xGEN_TWD18, :182 */
         if (dtw < sngl) return CM_SINGLE;             /* :184 */
         if (dtw < dbl) return CM_DBL18;               /* :226 */
-        if (dtw < trpl) return CM_TRPL18;             /* :266 */
+        /* :266; and its product slice dspP_M1(MAW+MBW-2 downto MBW-1) must exist in the 79 / 77-bit product
+         * (int_cmult_trpl18_dsp48.vhd:151-152, PWD :131-143): beyond that the entity does not elaborate */
+        if (dtw < trpl) return (dtw + twd - 2 <= trpl - 1) ? CM_TRPL18 : CM_NONE;
         return CM_NONE;
     }
     if (twd < twd_dsp) {                              /* xGEN_TWD25, :307 */
@@ -119,6 +121,14 @@ static void cmult(int64_t d_re, int64_t d_im, int64_t w_re, int64_t w_im,
                   int dtw, int twd, int xser_new, int64_t *o_re, int64_t *o_im)
 {
     const int v = cmult_variant(dtw, twd, xser_new);
+    if (v == CM_TRPL18) {
+        /* dspA_M1 <= SXT(M1_AA, AWD) with AWD = 61 / 59 (int_cmult_trpl18_dsp48.vhd:129, :161-162): the 61x18 / 59x18
+         * multiplier only ever sees the low AWD bits of the data operand, so a DTW above AWD is cut there.
+         * (Found by the primitive-level netlist in oracle/rtl/, tests/test_oracle_rtl.py.) */
+        const int awd = xser_new ? 61 : 59;
+        d_re = wrap_w(d_re, awd);
+        d_im = wrap_w(d_im, awd);
+    }
     *o_re = cmult_half(v, (i128)d_re * w_re, (i128)d_im * w_im, 1, dtw, twd, xser_new);
     *o_im = cmult_half(v, (i128)d_re * w_im, (i128)d_im * w_re, 0, dtw, twd, xser_new);
 }
@@ -278,6 +288,25 @@ int orc_twiddle(const orc_generics *g, int stage, int64_t k, int64_t *w_re, int6
 {
     if (!g || stage < 2 || stage > 19 || k < 0 || k >= ((int64_t)1 << stage)) return ORC_EINVAL;
     twiddle(stage, k, g->twdl_width, g->xser, w_re, w_im);
+    return ORC_OK;
+}
+
+/* Test hooks for tests/test_oracle_rtl.py: the multiplier and the butterflies on their own, so that they can
+ * be compared, operand by operand, with the DSP48-primitive-level transcription in oracle/rtl/. */
+int orc_cmult(int dtw, int twd, int xser_new, int64_t d_re, int64_t d_im, int64_t w_re, int64_t w_im,
+              int64_t *o_re, int64_t *o_im)
+{
+    if (cmult_variant(dtw, twd, xser_new) == CM_NONE || dtw > 64) return ORC_EINVAL;
+    cmult(d_re, d_im, w_re, w_im, dtw, twd, xser_new, o_re, o_im);
+    return ORC_OK;
+}
+
+/* one butterfly int_dif2_fly / int_dit2_fly (direction 0 / 1) of STAGE s at input width dtw, beat k; ab = {a_re, a_im,
+ * b_re, b_im} in and out; the twiddle is generated inside (rom_twiddle_int) */
+int orc_fly(const orc_generics *g, int s, int dtw, int64_t k, int64_t *ab)
+{
+    if (g->direction == 0) fly_dif(g, s, dtw, k, &ab[0], &ab[1], &ab[2], &ab[3]);
+    else fly_dit(g, s, dtw, k, &ab[0], &ab[1], &ab[2], &ab[3]);
     return ORC_OK;
 }
 

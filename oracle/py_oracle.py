@@ -113,6 +113,13 @@ def _half(p2: int, p1: int, sub: bool, dtw: int, twd: int, xser: int) -> int:
 
 
 def cmult(di_re: int, di_im: int, ww_re: int, ww_im: int, dtw: int, twd: int, xser: int):
+    if twd < 19 and (45 if xser else 43) <= dtw < (79 if xser else 77):
+        # trpl18: the 61x18 / 59x18 multiplier takes SXT(M1_AA, AWD) (int_cmult_trpl18_dsp48.vhd:161-162), so data
+        # wider than AWD is cut there, and the product slice (:151-152) must lie inside its 79 / 77 bits
+        awd, pwd = (61, 79) if xser else (59, 77)
+        if dtw + twd - 2 > pwd - 1:
+            raise ValueError("no multiplier generated (trpl18 product slice out of range)")
+        di_re, di_im = wrap(di_re, awd), wrap(di_im, awd)
     do_re = _half(di_re * ww_re, di_im * ww_im, True, dtw, twd, xser)    # xMDSP_RE, XALU "SUB"
     do_im = _half(di_re * ww_im, di_im * ww_re, False, dtw, twd, xser)   # xMDSP_IM, XALU "ADD"
     return do_re, do_im

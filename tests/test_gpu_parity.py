@@ -63,7 +63,8 @@ WIDTHS = [(8, 8, "NEW"), (12, 16, "OLD"), (18, 16, "NEW"), (18, 18, "NEW"), (24,
           (27, 16, "NEW"), (28, 16, "NEW"), (31, 12, "NEW"), (32, 16, "OLD"),
           (16, 19, "NEW"), (18, 24, "NEW"), (19, 25, "OLD"), (30, 27, "NEW"),          # TW >= 19: single25 / dbl35
           (36, 16, "NEW"), (40, 18, "NEW"), (44, 16, "OLD"), (45, 16, "NEW"), (50, 16, "NEW"),   # dbl18 / trpl18
-          (36, 22, "NEW"), (48, 19, "OLD"), (52, 27, "NEW"), (60, 16, "NEW"), (64, 10, "OLD")]
+          (36, 22, "NEW"), (48, 19, "OLD"), (52, 27, "NEW"), (60, 16, "NEW"), (64, 10, "OLD"),
+          (62, 16, "OLD"), (63, 16, "NEW"), (64, 8, "NEW")]   # trpl18 beyond its 59 / 61-bit data port (operand cut)
 
 
 @pytest.mark.parametrize("dw,tw,xser", WIDTHS)
@@ -75,6 +76,8 @@ def test_parity_widths_and_multiplier_variants(ib, oracle, dw, tw, xser, directi
             continue                                    # no trpl52 beyond 52 bits
         if dw + fmt * nfft + (rnd if not fmt else 0) > 64:
             continue                                    # beyond the 64-bit lanes
+        if ib.validate(ib.Generics(NFFT=nfft, DATA_WIDTH=dw, TWDL_WIDTH=tw, FORMAT=fmt, RNDMODE=rnd, XSER=xser), direction):
+            continue                                    # trpl18 product slice out of range: does not elaborate
         got, want = _run_both(ib, oracle, 9, seed=dw * 100 + tw, NFFT=nfft, DATA_WIDTH=dw, TWDL_WIDTH=tw,
                               FORMAT=fmt, RNDMODE=rnd, XSER=xser, direction=direction)
         assert np.array_equal(got, want), (fmt, rnd)
@@ -374,8 +377,11 @@ def test_invalid_generics_fail_like_elaboration(ib):
             ib.Core(ib.Generics(**base), 4, 0)
         assert ei.value.status == -1, kw
     with pytest.raises(ib.IntfftError) as ei:
-        ib.Core(ib.Generics(NFFT=10, DATA_WIDTH=60, FORMAT=1), 4, 0)
+        ib.Core(ib.Generics(NFFT=10, DATA_WIDTH=60, FORMAT=1, TWDL_WIDTH=8), 4, 0)
     assert ei.value.status == -4
+    with pytest.raises(ib.IntfftError) as ei:      # trpl18: product slice beyond the 79-bit product (does not elaborate)
+        ib.Core(ib.Generics(NFFT=10, DATA_WIDTH=60, FORMAT=1), 4, 0)
+    assert ei.value.status == -1
 
 
 def test_device_stimulus_and_checksum_match_oracle(ib, oracle):

@@ -64,11 +64,19 @@ def test_cross_wide_data(direction, xser):
     """dbl18 (28/26..44/42 bits) and trpl18 (>= 45/43 bits) data paths."""
     rng = random.Random(5 + direction + 2 * xser)
     for dw, tw, fmt, rnd in [(26, 16, 0, 0), (28, 16, 1, 0), (40, 18, 0, 1), (43, 8, 0, 0), (45, 16, 0, 0),
-                             (50, 17, 1, 0), (58, 16, 1, 0), (63, 16, 0, 1), (64, 10, 0, 0)]:
+                             (50, 17, 1, 0), (58, 16, 1, 0), (62, 16, 0, 0), (63, 16, 0, 1), (64, 10, 0, 0)]:
         if direction == 0 and fmt == 1 and rnd == 1:
             continue
         gd = dict(nfft_log2=6, data_width=dw, twdl_width=tw, format=fmt, rndmode=rnd, xser=xser,
                   use_fly=1, direction=direction)
+        # trpl18 beyond its 61 / 59-bit data port cuts the operand (62 / 63 / 64-bit cases), and beyond
+        # DTW + TWD - 2 = 78 / 76 its product slice does not exist: (63, 16) elaborates for XSER NEW only
+        if co.validate(co.generics(**gd)) != 0:
+            # only (58 unscaled DIT, OLD) and (63, OLD) may be refused here, both for the trpl18 slice rule
+            assert co.validate(co.generics(**gd)) == -1 and xser == 0 and dw in (58, 63)
+            with pytest.raises(ValueError):
+                po.transform(po.Generics(**gd), _frame(rng, 64, dw))
+            continue
         _both(gd, _frame(rng, 64, dw))
 
 
@@ -112,13 +120,14 @@ def test_validate_mirrors_elaboration():
            dict(twdl_width=26, xser=0), dict(data_width=7), dict(format=2), dict(rndmode=2), dict(xser=2),
            dict(direction=3), dict(format=1, rndmode=1, direction=0),       # wz_re double driver
            dict(twdl_width=20, data_width=53),                              # no trpl52 beyond 52 bits
-           dict(twdl_width=20, data_width=40, format=1, nfft_log2=16)]      # grows past 52 bits
+           dict(twdl_width=20, data_width=40, format=1, nfft_log2=16),      # grows past 52 bits
+           dict(data_width=60, format=1, nfft_log2=10)]                     # trpl18 product slice beyond bit 78
     for b in bad:
         d = dict(ok); d.update(b)
         assert co.validate(co.generics(**d)) == -1, b
     d = dict(ok); d.update(format=1, rndmode=1, direction=1)                # DIT: elaborates as unscaled
     assert co.validate(co.generics(**d)) == 0
-    d = dict(ok); d.update(data_width=60, format=1, nfft_log2=10)           # legal upstream, > 64-bit lanes
+    d = dict(ok); d.update(data_width=60, format=1, nfft_log2=10, twdl_width=8)   # legal upstream, > 64-bit lanes
     assert co.validate(co.generics(**d)) == -4
 
 
