@@ -16,7 +16,7 @@
 // nor a GPU — the counterpart of reading the synthesis log for the multiplier / buffer variants generated.
 //
 // usage: intfft_host [--ifft | --pair] [--nfft N] [--dw W] [--tw W] [--mode UNSCALED|ROUNDING|TRUNCATE]
-//                    [--xser OLD|NEW] [--no-fly] [--lanes] [--top17] <in.dat> <out.dat>
+//                    [--xser OLD|NEW] [--no-fly | --no-fly-fwd] [--no-fly-inv] [--lanes] [--top17] <in.dat> <out.dat>
 //        intfft_host --describe [--ifft] [--nfft N] [--dw W] [--tw W] [--mode ...] [--xser ...]
 #include <cstdio>
 #include <cstdlib>
@@ -26,38 +26,10 @@
 
 #include "intfft.h"
 
-// int_fft_ifft_pair through host buffers, using only the C-ABI: device staging comes from two throw-away
-// one-core plans' exec_host (FFT to host, IFFT from host) when no CUDA runtime is linked into this tool.
-static int run_pair_host(intfft_pair *, const intfft_layout &lay, const void *h_in, void *h_out);
-
 static int fail(const char *what, int st)
 {
     std::fprintf(stderr, "intfft_host: %s: %s\n", what, intfft_strerror(st));
     return 1;
-}
-
-static intfft_generics g_for_pair;
-static long long frames_for_pair;
-static int run_pair_host(intfft_pair *, const intfft_layout &lay, const void *h_in, void *h_out)
-{
-    intfft_generics gf = g_for_pair, gi = g_for_pair;
-    gf.direction = 0;
-    gi.direction = 1;
-    gi.data_width = gf.data_width + gf.format * gf.nfft_log2;        // int_fft_ifft_pair.vhd:261
-    intfft_plan *pf = nullptr, *pi = nullptr;
-    int st = intfft_plan_create(&pf, &gf, frames_for_pair, 0);
-    if (!st) st = intfft_plan_create(&pi, &gi, frames_for_pair, 0);
-    if (!st) {
-        intfft_layout lf;
-        intfft_query(pf, &lf);
-        std::vector<unsigned char> mid((size_t)lf.out_bytes);
-        st = intfft_exec_host(pf, h_in, mid.data());
-        if (!st) st = intfft_exec_host(pi, mid.data(), h_out);
-    }
-    if (pf) intfft_plan_destroy(pf);
-    if (pi) intfft_plan_destroy(pi);
-    (void)lay;
-    return st;
 }
 
 int main(int argc, char **argv)
@@ -65,6 +37,7 @@ int main(int argc, char **argv)
     intfft_generics g{7, 16, 16, 1, 0, 1, 1, 0};   // the testbench defaults: NFFT=7, 16/16, XSERIES="NEW"
     std::string in_path, out_path;
     bool lanes = false, top17 = false, pair = false, describe = false;
+    int fly_inv = 1;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&](const char *name) -> const char * {
@@ -80,7 +53,8 @@ int main(int argc, char **argv)
         else if (a == "--dw") g.data_width = std::atoi(next("--dw"));
         else if (a == "--tw") g.twdl_width = std::atoi(next("--tw"));
         else if (a == "--xser") g.xser = std::strcmp(next("--xser"), "OLD") ? 1 : 0;
-        else if (a == "--no-fly") g.use_fly = 0;
+        else if (a == "--no-fly" || a == "--no-fly-fwd") g.use_fly = 0;      // USE_FLY / FLY_FWD = '0'
+        else if (a == "--no-fly-inv") fly_inv = 0;                            // FLY_INV = '0' (--pair only)
         else if (a == "--mode") {
             std::string m = next("--mode");                 // set_mode, tb/fft_signle_test.vhd:81-88
             if (m == "UNSCALED") { g.format = 1; g.rndmode = 0; }
@@ -133,13 +107,11 @@ int main(int argc, char **argv)
     const long long frames = (long long)vals.size() / (2 * n);
     if (frames < 1) { std::fprintf(stderr, "need at least one frame of %lld samples\n", n); return 1; }
 
-    g_for_pair = g;
-    frames_for_pair = frames;
     intfft_plan *plan = nullptr;
     intfft_pair *pr = nullptr;
     intfft_layout lay;
     if (pair) {
-        st = intfft_pair_create(&pr, &g, 1, frames, 0);
+        st = intfft_pair_create(&pr, &g, fly_inv, frames, 0);
         if (st) return fail("pair_create", st);
         intfft_pair_query(pr, &lay);
     } else {
@@ -153,7 +125,7 @@ int main(int argc, char **argv)
         else if (lay.in_scalar_bytes == 4) reinterpret_cast<int32_t *>(hin.data())[i] = (int32_t)vals[i];
         else reinterpret_cast<int64_t *>(hin.data())[i] = vals[i];
     }
-    if (pair) st = run_pair_host(pr, lay, hin.data(), hout.data());
+    if (pair) st = intfft_pair_exec_host(pr, hin.data(), hout.data());     // the spectrum stays on the device
     else st = intfft_exec_host(plan, hin.data(), hout.data());
     if (st) return fail("exec", st);
     auto out_scalar = [&](long long i) -> long long {

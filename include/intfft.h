@@ -86,8 +86,8 @@ int intfft_plan_destroy(intfft_plan *p);
 int intfft_query(const intfft_plan *p, intfft_layout *l);
 
 /* Run `batch` frames. d_in / d_out are DEVICE pointers in the flat layout above; asynchronous on
- * `cuda_stream` (a cudaStream_t, NULL = default stream).  Plans with two passes (NFFT >= 13 mostly) run the
- * batch in groups of frames small enough for the intermediate to stay in the L2 cache between the passes. d_in == d_out is allowed when the input
+ * `cuda_stream` (a cudaStream_t, NULL = default stream).  (Environment knob INTFFT_GROUP_MB=<n>: run a two-pass plan
+ * in groups of frames whose intermediate fits n MB of L2; off by default — as separate launches it measured slower.) d_in == d_out is allowed when the input
  * and output containers have the same size. Both pointers must be 16-byte aligned (the kernels move
  * frames with 16-byte vector and TMA bulk accesses; cudaMalloc memory and any whole-frame offset into
  * it qualify), otherwise INTFFT_EINVAL. Replaces driving DI_RE0/IM0/RE1/IM1 + DI_ENA and

@@ -61,6 +61,16 @@ def lib() -> ctypes.CDLL:
         L.intfft_pair_destroy.argtypes = [vp]
         L.intfft_pair_query.argtypes = [vp, P(_CLayout)]
         L.intfft_pair_exec.argtypes = [vp, vp, vp, vp]
+        L.intfft_pair_exec_host.argtypes = [vp, vp, vp]
+        L.intfft_host_alloc.argtypes = [P(vp), ctypes.c_size_t]
+        L.intfft_host_free.argtypes = [vp]
+        L.intfft_multi_create.argtypes = [P(vp), P(_CGenerics), ctypes.c_int64, P(ctypes.c_int), ctypes.c_int]
+        L.intfft_multi_destroy.argtypes = [vp]
+        L.intfft_multi_devices.argtypes = [vp]
+        L.intfft_multi_query.argtypes = [vp, P(_CLayout)]
+        L.intfft_multi_shard.argtypes = [vp, ctypes.c_int, P(ctypes.c_int), P(ctypes.c_int64), P(ctypes.c_int64)]
+        L.intfft_multi_exec_host.argtypes = [vp, vp, vp]
+        L.intfft_multi_exec.argtypes = [vp, P(vp), P(vp), P(vp)]
         L.intfft_bitrev.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, vp, vp, ctypes.c_int, vp]
         L.intfft_fill_random.argtypes = [vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
                                          ctypes.c_int, vp]
@@ -177,14 +187,21 @@ class Core:
         import torch
         return torch.empty((self.batch, self.n, 2), dtype=_torch_dtype(self.out_dtype), device=f"cuda:{self.device}")
 
+    def _check(self, d_in, d_out):
+        """Device tensors handed to the C-ABI: right device, contiguous, right element size and count (a wrong
+        tensor would otherwise become an out-of-bounds device access inside a kernel)."""
+        for t, sb, what in ((d_in, self.layout.in_scalar_bytes, "input"), (d_out, self.layout.out_scalar_bytes, "output")):
+            if not (t.is_cuda and t.device.index == self.device and t.is_contiguous()):
+                raise IntfftError(EINVAL, f"{what} tensor must be contiguous on cuda:{self.device}")
+            if t.numel() != self.batch * self.n * 2 or t.element_size() != sb:
+                raise IntfftError(EINVAL, f"{what} tensor must hold {self.batch} x {self.n} x 2 scalars of {sb} bytes")
+
     def exec(self, d_in, d_out=None, stream=None):
         """Run the batch on device tensors shaped [batch, N, 2] ({re, im} interleaved)."""
         import torch
         if d_out is None:
             d_out = self.new_output()
-        assert d_in.is_cuda and d_out.is_cuda and d_in.is_contiguous() and d_out.is_contiguous()
-        assert d_in.numel() == self.batch * self.n * 2 and d_out.numel() == self.batch * self.n * 2
-        assert d_in.element_size() == self.layout.in_scalar_bytes and d_out.element_size() == self.layout.out_scalar_bytes
+        self._check(d_in, d_out)
         s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
         st = lib().intfft_exec(self._h, d_in.data_ptr(), d_out.data_ptr(), s)
         if st:
@@ -196,7 +213,9 @@ class Core:
         import torch
         if d_out is None:
             d_out = self.new_output()
-        assert d_in.is_cuda and d_in.is_contiguous() and d_in.data_ptr() != d_out.data_ptr()
+        self._check(d_in, d_out)
+        if d_in.data_ptr() == d_out.data_ptr():
+            raise IntfftError(EINVAL, "exec_natural is out of place")
         s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
         st = lib().intfft_exec_natural(self._h, d_in.data_ptr(), d_out.data_ptr(), s)
         if st:
@@ -248,13 +267,101 @@ class Pair:
         import torch
         if d_out is None:
             d_out = torch.empty((self.batch, self.n, 2), dtype=_torch_dtype(self.out_dtype), device=d_in.device)
-        assert d_in.is_cuda and d_in.is_contiguous() and d_in.element_size() == self.layout.in_scalar_bytes
-        assert d_out.element_size() == self.layout.out_scalar_bytes and d_out.numel() == self.batch * self.n * 2
+        for t, sb, what in ((d_in, self.layout.in_scalar_bytes, "input"), (d_out, self.layout.out_scalar_bytes, "output")):
+            if not (t.is_cuda and t.device.index == self.device and t.is_contiguous()):
+                raise IntfftError(EINVAL, f"{what} tensor must be contiguous on cuda:{self.device}")
+            if t.numel() != self.batch * self.n * 2 or t.element_size() != sb:
+                raise IntfftError(EINVAL, f"{what} tensor must hold {self.batch} x {self.n} x 2 scalars of {sb} bytes")
         s = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
         st = lib().intfft_pair_exec(self._h, d_in.data_ptr(), d_out.data_ptr(), s)
         if st:
             raise IntfftError(st, "intfft_pair_exec")
         return d_out
+
+    def exec_host(self, x: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """tb/fft_double_test.vhd semantics through host buffers; the spectrum never leaves the device."""
+        x = np.ascontiguousarray(x, self.in_dtype).reshape(self.batch, self.n, 2)
+        if out is None:
+            out = np.empty((self.batch, self.n, 2), self.out_dtype)
+        assert out.dtype == self.out_dtype and out.flags.c_contiguous and out.size == x.size
+        st = lib().intfft_pair_exec_host(self._h, x.ctypes.data, out.ctypes.data)
+        if st:
+            raise IntfftError(st, "intfft_pair_exec_host")
+        return out
+
+
+class Multi:
+    """One process, several devices: the batch is cut into contiguous shards (shard_range), one per device, and
+    every device runs the same int_fftNk / int_ifftNk plan on its shard — no exchange step."""
+
+    def __init__(self, generics: Generics, batch: int, direction: int = 0, devices=(0,)):
+        self.generics, self.direction, self.devices = generics, direction, list(devices)
+        self._h = ctypes.c_void_p()
+        c = generics.c_struct(direction)
+        arr = (ctypes.c_int * len(self.devices))(*self.devices)
+        st = lib().intfft_multi_create(ctypes.byref(self._h), ctypes.byref(c), batch, arr, len(self.devices))
+        if st:
+            self._h = ctypes.c_void_p()
+            raise IntfftError(st, "intfft_multi_create")
+        lay = _CLayout()
+        lib().intfft_multi_query(self._h, ctypes.byref(lay))
+        self.layout, self.n, self.batch = lay, int(lay.n), int(lay.batch)
+        self.in_dtype, self.out_dtype = scalar_dtype(lay.in_width), scalar_dtype(lay.out_width)
+
+    def shards(self):
+        out = []
+        for i in range(lib().intfft_multi_devices(self._h)):
+            dev, first, frames = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
+            lib().intfft_multi_shard(self._h, i, ctypes.byref(dev), ctypes.byref(first), ctypes.byref(frames))
+            out.append((dev.value, first.value, frames.value))
+        return out
+
+    def exec_host(self, x: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        x = np.ascontiguousarray(x, self.in_dtype).reshape(self.batch, self.n, 2)
+        if out is None:
+            out = np.empty((self.batch, self.n, 2), self.out_dtype)
+        assert out.dtype == self.out_dtype and out.flags.c_contiguous and out.size == x.size
+        self.exec_host_ptr(x.ctypes.data, out.ctypes.data)
+        return out
+
+    def exec_host_ptr(self, h_in_ptr: int, h_out_ptr: int):
+        st = lib().intfft_multi_exec_host(self._h, h_in_ptr, h_out_ptr)
+        if st:
+            raise IntfftError(st, "intfft_multi_exec_host")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().intfft_multi_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+
+class HostBuffer:
+    """Page-locked host memory from intfft_host_alloc (portable across devices), viewed as a NumPy array."""
+
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._p = ctypes.c_void_p()
+        st = lib().intfft_host_alloc(ctypes.byref(self._p), self.nbytes)
+        if st:
+            self._p = ctypes.c_void_p()
+            raise IntfftError(st, "intfft_host_alloc")
+        buf = (ctypes.c_char * self.nbytes).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    @property
+    def ptr(self) -> int:
+        return self._p.value
+
+    def close(self):
+        if getattr(self, "_p", None) and self._p.value:
+            self.array = None
+            lib().intfft_host_free(self._p)
+            self._p = ctypes.c_void_p()
+
+    __del__ = close
 
 
 def _torch_dtype(np_dtype):

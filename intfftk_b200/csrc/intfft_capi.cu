@@ -185,6 +185,25 @@ int upload_twiddles(Plan &pl)
             pl.lw32_r[(1 << s) - 1 + k] = tab[((size_t)1 << s) + k].x;
             pl.lw32_i[(1 << s) - 1 + k] = tab[((size_t)1 << s) + k].y;
         }
+    if (!pl.passes.empty() && pl.passes[0].path == 2 && pl.mode == MODE_TRUNC && pl.g.twdl_width < 19) {
+        // 32-bit-lane TRUNCATE kernels (KIND_SINGLE_PRE): W << e with e = 31 - sh_single = 32 - TWDL_WIDTH puts the
+        // multiplier's output slice at bit 32 of the 64-bit sum of products; a twiddle is a TWDL_WIDTH-bit two's
+        // complement number, so W << e always fits an int32.  (Not for TWDL_WIDTH >= 19: there the slice starts one bit
+        // lower relative to the container, sh_single = TWDL_WIDTH - 2, and the Taylor refinement can push |W| to
+        // 2^(TWDL_WIDTH-2) and beyond, which W << (33 - TWDL_WIDTH) would no longer hold.)
+        const CmultConsts cm = cmult_consts(pl.g.twdl_width, pl.g.xser);
+        const int e = 31 - cm.sh_single;
+        std::vector<int2> tp(cnt);
+        for (size_t i = 0; i < cnt; ++i)
+            tp[i] = make_int2((int)((unsigned)tab[i].x << e), (int)((unsigned)tab[i].y << e));
+        for (int s = 2; s <= 3 && s < n; ++s)
+            for (int k = 0; k < (1 << s); ++k) {
+                pl.lwp32_r[(1 << s) - 1 + k] = tp[(1 << s) + k].x;
+                pl.lwp32_i[(1 << s) - 1 + k] = tp[(1 << s) + k].y;
+            }
+        if (cudaMalloc(&pl.d_twp32, cnt * sizeof(int2)) != cudaSuccess) return INTFFT_ENOMEM;
+        if (cudaMemcpy(pl.d_twp32, tp.data(), cnt * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) return INTFFT_ECUDA;
+    }
     if (!pl.passes.empty() && pl.passes[0].path == 1) {
         // 32-bit-product kernel: W << e with e = 33 - TWDL_WIDTH - DATA_WIDTH puts the multiplier's
         // output slice P(DTW+TWD-2 downto TWD-1) (int_cmult_dsp48.vhd:189-190) at bits 31 .. 32-DTW
@@ -226,7 +245,10 @@ static bool batch_ok(int64_t batch, int nfft_log2) { return batch >= 1 && batch 
 static long long pick_group_frames(const Plan &pl)
 {
     if (pl.passes.size() != 2) return 0;
-    long long mb = 24;
+    // Measured (profiles/r02/group_sweep_multilaunch.jsonl): as separate launches per group this LOSES on every
+    // two-pass plan — c4 1.28 -> 1.77 ms at 64 MB groups, 3.7 ms at 8 MB — because a launch boundary costs 10-15 us of
+    // drain / ramp / per-unit twiddle loads against 20-80 us of work per group.  Off unless asked for.
+    long long mb = 0;
     if (const char *e = std::getenv("INTFFT_GROUP_MB")) mb = std::atoll(e);
     if (mb <= 0) return 0;
     const PassParams &a = pl.passes[0].kp, &b = pl.passes[1].kp;
@@ -297,6 +319,7 @@ int intfft_plan_destroy(intfft_plan *p)
     DeviceGuard guard(p->device);
     cudaFree(p->d_tw);
     cudaFree(p->d_twp);
+    cudaFree(p->d_twp32);
     cudaFree(p->scratch[0]);
     cudaFree(p->scratch[1]);
     cudaFree(p->nat);
@@ -342,7 +365,8 @@ static int run_pass(const intfft_plan *p, size_t i, const void *in, void *out, l
         e = pd.kp.c > 0 ? launch_fast16_strided(pd, p->mode, dit, p->d_twp, p->num_sms, cuda_stream)
                         : launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream);
     else if (pd.path == 2)
-        e = launch_fast32(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
+        e = launch_fast32(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream, p->d_twp32,
+                          p->lwp32_r, p->lwp32_i);
     else if (pd.path == 3)
         e = launch_fast64(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
     else if (pd.path == 4)
@@ -523,6 +547,7 @@ struct intfft_pair {
     intfft_plan *fwd = nullptr, *inv = nullptr;
     void *mid = nullptr;           // spectrum between the two cores (bit-reversed order), device
     long long mid_frames = 0;      // frames `mid` holds: the pair runs group by group so the spectrum stays in L2
+    bool fused = false;            // both cores in one kernel (packed-16 plans of 2^8 .. 2^12 points): no `mid` at all
     HostPipe pipe;
 };
 
@@ -542,11 +567,15 @@ int intfft_pair_create(intfft_pair **out, const intfft_generics *g, int fly_inv,
     if (!p) return INTFFT_ENOMEM;
     st = intfft_plan_create(&p->fwd, &gf, batch, device);
     if (!st) st = intfft_plan_create(&p->inv, &gi, batch, device);
-    if (!st) {
+    if (!st && gf.use_fly && gi.use_fly && fast16_pair_supported(gf) && fast16_supported(gi) && gi.data_width == gf.data_width &&
+        p->fwd->passes.size() == 1 && p->fwd->passes[0].path == 1 && !std::getenv("INTFFT_PAIR_UNFUSED")) {
+        p->fused = true;           // the spectrum stays in registers between the two cores (intfft_fast16.cu, PAIR)
+        p->mid_frames = batch;
+    } else if (!st) {
         DeviceGuard guard(device);
         // the spectrum of one group of frames: small enough to be read back from L2 by the inverse core
         const long long frame_bytes = (1ll << g->nfft_log2) * 2 * p->fwd->out_sb;
-        long long mb = 32;
+        long long mb = 0;          // whole batch: per-group launches measured slower (see pick_group_frames)
         if (const char *e = std::getenv("INTFFT_PAIR_GROUP_MB")) mb = std::atoll(e);
         long long gfm = mb > 0 ? (mb << 20) / frame_bytes : batch;
         if (gfm < 1) gfm = 1;
@@ -583,13 +612,21 @@ int intfft_pair_query(const intfft_pair *p, intfft_layout *l)
     l->out_width = b.out_width;
     l->out_scalar_bytes = b.out_scalar_bytes;
     l->out_bytes = b.out_bytes;
-    l->n_passes = a.n_passes + b.n_passes;
+    l->n_passes = p->fused ? 1 : a.n_passes + b.n_passes;
     l->lane_bits = a.lane_bits > b.lane_bits ? a.lane_bits : b.lane_bits;
     return INTFFT_OK;
 }
 
 static int pair_frames(const intfft_pair *p, const void *d_in, void *d_out, long long frames, void *cuda_stream)
 {
+    if (p->fused) {
+        const intfft_plan *f = p->fwd;
+        PassDesc pd = f->passes[0];
+        pd.kp.in = d_in;
+        pd.kp.out = d_out;
+        pd.kp.total = frames << f->g.nfft_log2;
+        return launch_fast16_pair(pd, f->mode, f->d_twp, f->lw_r, f->lw_i, f->num_sms, cuda_stream) ? INTFFT_ECUDA : INTFFT_OK;
+    }
     const long long n = 1ll << p->fwd->g.nfft_log2;
     const long long in_frame = n * 2 * p->fwd->in_sb, out_frame = n * 2 * p->inv->out_sb;
     for (long long f0 = 0; f0 < frames; f0 += p->mid_frames) {

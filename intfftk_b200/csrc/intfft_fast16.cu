@@ -24,6 +24,8 @@
 //     pattern (32-bit at stride 256 / 16, 128-bit contiguous) is bank-conflict free for N = 4096.
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "intfft_internal.h"
 
 namespace intfft {
@@ -244,10 +246,15 @@ struct TwSmem {          // table[w][tid & 15] of pre-shifted (re, im); one LDS.
 // The landing buffer of the NEXT tile doubles as the previous tile's scatter buffer, so in this variant
 // the TMA prefetch is issued after the tile's first CTA barrier (every thread has then left the
 // previous tile) instead of at the top of the tile.
-template <int NLOG2, bool DIT, bool DW16, bool MIDSM, int MODE, bool NAT = false>
+// PAIR (f2, int_fft_ifft_pair, main/int_fft_ifft_pair.vhd:209-283): int_fftNk and int_ifftNk in ONE kernel.  The
+// FFT's last round leaves a thread with 16 contiguous samples of the bit-reversed spectrum — exactly what the IFFT's
+// first round owns — so the spectrum never leaves the registers: the DIF chain runs without its output side, the
+// DIT chain without its input side (same twiddle tables: W_s[k] does not depend on the direction).
+template <int NLOG2, bool DIT, bool DW16, bool MIDSM, int MODE, bool NAT = false, bool PAIR = false>
 __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid_constant__ Fast16Params p)
 {
     static_assert(!NAT || (NLOG2 == 12 && !DIT), "fused natural-order output: 4096-point DIF only");
+    static_assert(!PAIR || (!DIT && !NAT && NLOG2 >= 8), "pair: instantiated as the DIF kernel, 2^8 .. 2^12 points");
     constexpr int R0 = ((NLOG2 - 1) % 4) + 1;      // stages in the lowest round
     constexpr int NR = 1 + (NLOG2 - R0) / 4;       // rounds; round r > 0 covers bits R0+4(r-1) .. +3
     static_assert(NR >= 1 && NR <= 3, "supported: 2^3 .. 2^12 points");
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
     constexpr bool TMA_IN = !DIT;                  // DIF: first round reads stride-256 words -> stage via TMA
     // DIF, 4-stage last round: results go back into the thread's own tile slots and leave warp-coalesced
     // (stored directly, a warp instruction would write 32 separate 16-byte pieces at a 64-byte pitch)
-    constexpr bool COALESCE = (!DIT || NR == 1) && !NAT;   // (a one-round DIT ends in the lowest round as well)
+    // (COALESCE is decided per chain below: (!DIT || NR == 1) && !NAT — a one-round DIT ends in the lowest round as well)
     // DIT, 4-stage first round: a thread needs its own 16 contiguous samples (64 bytes).  Loaded directly, a
     // warp instruction would touch 32 separate 16-byte pieces at a 64-byte pitch, so the WARP fetches its
     // 2 KB as 512 contiguous bytes per cp.async instruction into a skewed landing tile, one tile ahead.
@@ -363,9 +370,17 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
         }
 
         int re[16], im[16];
+        // one stage chain over the tile.  PH 0: the plain kernel; PH 1: first chain of a pair (DIF, results stay in
+        // the registers); PH 2: second chain of a pair (DIT, first round's samples are already in the registers)
+        auto chain = [&](auto dir_tag, auto ph_tag) {
+        constexpr bool CD = decltype(dir_tag)::value;         // this chain's direction
+        constexpr int PH = decltype(ph_tag)::value;
+        constexpr bool TMA_IN = !CD && PH != 2;
+        constexpr bool CP_IN = CD && PH == 0;
+        constexpr bool COALESCE = (!CD || NR == 1) && !NAT && PH == 0;
 #pragma unroll
         for (int rr = 0; rr < NR; ++rr) {
-            const int r = DIT ? rr : NR - 1 - rr;                 // DIF walks the bits downwards
+            const int r = CD ? rr : NR - 1 - rr;                 // DIF walks the bits downwards
             const int lo = r == 0 ? 0 : R0 + 4 * (r - 1);
             const int R = r == 0 ? R0 : 4;
             const bool first = rr == 0, last = rr == NR - 1;
@@ -373,14 +388,16 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
             const unsigned pbase = phys(base);
 
             // ---- fetch 16 samples ----
-            if (r == 0 && R0 == 4) {
+            if (PH == 2 && first) {
+                // the spectrum is already here: DIF's lowest round and CD's lowest round own the same 16 samples
+            } else if (r == 0 && R0 == 4) {
                 if (first && CP_IN) { cp_async_wait_group0(); __syncwarp(); }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint4 v;
                     if (first && TMA_IN) {                        // 16-point DIF: straight from the (linear) TMA landing buffer
                         v = *reinterpret_cast<const uint4 *>(stage[it & 1] + 16 * tid + 4 * c);
-                    } else if (first) {                           // DIT: this thread's 64 bytes of the landed tile
+                    } else if (first) {                           // CD: this thread's 64 bytes of the landed tile
                         v = *reinterpret_cast<const uint4 *>(land + pbase + phys(4 * c));
                     } else {
                         v = *reinterpret_cast<const uint4 *>(sm + pbase + phys(4 * c));
@@ -408,7 +425,7 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                     const unsigned off = ((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R));
                     uint32_t x;
                     if (first && TMA_IN) x = stage[it & 1][base + off];
-                    else if (first) x = land[pbase + phys(off)];          // DIT: landed by the warp (zero-filled past the end)
+                    else if (first) x = land[pbase + phys(off)];          // CD: landed by the warp (zero-filled past the end)
                     else x = sm[pbase + phys(off)];
                     if (first) unpack<DW16>(x, p.dw, re[m], im[m]);
                     else unpack<true>(x, p.dw, re[m], im[m]);
@@ -422,14 +439,16 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
             // ---- butterflies ----
             // DIF upper rounds end with a multiply stage on register bit 0 (global bit >= 2): odd registers
             // then hold raw products and are packed from their upper half-words
-            constexpr bool RAW = !DIT && DW16 && R0 >= 2;
-            if (r == 0) round_regs<0, R0, DIT, DW16, MODE, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
-            else if (r == 1 && MIDSM) round_regs<R0, 4, DIT, DW16, MODE, RAW>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
-            else if (r == 1) round_regs<R0, 4, DIT, DW16, MODE, RAW>(re, im, TwRegs{uwr[0], uwi[0]}, tid_odd, sh_full, sh_half);
-            else round_regs<R0 + 4, 4, DIT, DW16, MODE, RAW>(re, im, TwRegs{uwr[NU - 1], uwi[NU - 1]}, tid_odd, sh_full, sh_half);
+            constexpr bool RAW = !CD && DW16 && R0 >= 2;
+            if (r == 0) round_regs<0, R0, CD, DW16, MODE, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
+            else if (r == 1 && MIDSM) round_regs<R0, 4, CD, DW16, MODE, RAW>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
+            else if (r == 1) round_regs<R0, 4, CD, DW16, MODE, RAW>(re, im, TwRegs{uwr[0], uwi[0]}, tid_odd, sh_full, sh_half);
+            else round_regs<R0 + 4, 4, CD, DW16, MODE, RAW>(re, im, TwRegs{uwr[NU - 1], uwi[NU - 1]}, tid_odd, sh_full, sh_half);
 
             // ---- hand the samples on: to the exchange tile, or to HBM after the last round ----
-            if (r == 0 && R0 == 4) {
+            if (PH == 1 && last) {
+                // first chain of a pair: nothing leaves the registers
+            } else if (r == 0 && R0 == 4) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint4 v = make_uint4(pack(re[4 * c], im[4 * c]), pack(re[4 * c + 1], im[4 * c + 1]),
@@ -465,8 +484,10 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
             // The hand-over between the two LOWEST rounds of the 4+4+4 schedule stays inside a warp
             // (round bits 7..4 <-> 3..0 both keep tid >> 5 fixed), so a warp barrier is enough there;
             // the double-buffered tile makes one CTA barrier per frame sufficient for reuse safety.
-            if (!last) {
-                const bool warp_local = (NR == 3 && R0 == 4) && ((DIT && rr == 0) || (!DIT && rr == 1));
+            if (PH == 1 && last) {
+                // (pair: the inverse chain follows)
+            } else if (!last) {
+                const bool warp_local = (NR == 3 && R0 == 4) && ((CD && rr == 0) || (!CD && rr == 1));
                 if (warp_local) __syncwarp();
                 else __syncthreads();
                 if (NAT && rr == 0) prefetch_next();
@@ -484,6 +505,16 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
 #pragma unroll
                 for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(p.out + g0 + 4 * (tid + 256 * c)) = nb[256 * c];
             }
+        }
+        };
+        if (!PAIR) {
+            chain(std::integral_constant<bool, DIT>{}, std::integral_constant<int, 0>{});
+        } else {
+            chain(std::false_type{}, std::integral_constant<int, 1>{});
+            // every lane of the warp has read its round-0 samples of the forward chain out of the warp's region of
+            // the exchange tile before the inverse chain's round 0 writes its results there
+            __syncwarp();
+            chain(std::true_type{}, std::integral_constant<int, 2>{});
         }
     }
 }
@@ -648,12 +679,12 @@ cudaError_t launch_strided_k(const Strided16Params &p, int mode, int grid, cudaS
     return cudaGetLastError();
 }
 
-template <int NLOG2, bool DIT, bool DW16, bool NAT = false>
+template <int NLOG2, bool DIT, bool DW16, bool NAT = false, bool PAIR = false>
 cudaError_t launch_k(const Fast16Params &p, int mode, int grid, cudaStream_t st)
 {
     const int smem = kSmemHead + 2 * kTileWords * 4 + (DIT ? (int)kTileWords * 4 : 2 * 4096 * 4);
     constexpr bool MIDSM = (NLOG2 == 12);
-    auto k = mode == MODE_ROUND ? fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_ROUND, NAT> : fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_TRUNC, NAT>;
+    auto k = mode == MODE_ROUND ? fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_ROUND, NAT, PAIR> : fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_TRUNC, NAT, PAIR>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, smem, st>>>(p);
@@ -747,6 +778,49 @@ int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const
         if (pd.natural && !dit) e = dw16 ? launch_k<12, false, true, true>(p, mode, (int)grid, st) : launch_k<12, false, false, true>(p, mode, (int)grid, st);
         else e = launch_n<12>(p, mode, dit, dw16, (int)grid, st);
         break;
+    default: e = cudaErrorInvalidValue; break;
+    }
+    count_launch();
+    return (int)e;
+}
+
+// f2: int_fftNk -> int_ifftNk of a packed-16 plan (2^8 .. 2^12 points, both cores on) as ONE kernel
+bool fast16_pair_supported(const intfft_generics &g)
+{
+    return fast16_supported(g) && g.nfft_log2 >= 8 && g.nfft_log2 <= 12;
+}
+
+template <int NLOG2>
+static cudaError_t launch_pair_n(const Fast16Params &p, int mode, bool dw16, int grid, cudaStream_t st)
+{
+    return dw16 ? launch_k<NLOG2, false, true, false, true>(p, mode, grid, st) : launch_k<NLOG2, false, false, false, true>(p, mode, grid, st);
+}
+
+int launch_fast16_pair(const PassDesc &pd, int mode, const int2 *twp, const int *lw_r, const int *lw_i, int num_sms,
+                       void *stream)
+{
+    Fast16Params p{};
+    p.in = reinterpret_cast<const uint32_t *>(pd.kp.in);
+    p.out = reinterpret_cast<uint32_t *>(pd.kp.out);
+    p.twp = twp;
+    p.total = pd.kp.total;
+    p.n_tiles = (pd.kp.total + 4095) >> 12;
+    p.dw = pd.kp.dw;
+    p.sh_full = 32 - p.dw;
+    p.sh_half = 33 - p.dw;
+    for (int i = 0; i < 16; ++i) { p.lw_r[i] = lw_r[i]; p.lw_i[i] = lw_i[i]; }
+    long long grid = (pd.kp.g == 12 ? 3ll : 2ll) * num_sms;
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    if (grid < 1) grid = 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool dw16 = p.dw == 16;
+    cudaError_t e;
+    switch (pd.kp.g) {
+    case 8: e = launch_pair_n<8>(p, mode, dw16, (int)grid, st); break;
+    case 9: e = launch_pair_n<9>(p, mode, dw16, (int)grid, st); break;
+    case 10: e = launch_pair_n<10>(p, mode, dw16, (int)grid, st); break;
+    case 11: e = launch_pair_n<11>(p, mode, dw16, (int)grid, st); break;
+    case 12: e = launch_pair_n<12>(p, mode, dw16, (int)grid, st); break;
     default: e = cudaErrorInvalidValue; break;
     }
     count_launch();

@@ -54,7 +54,12 @@ struct V {
 __device__ __forceinline__ V mk(int f) { return V{f, f >> 1}; }
 
 // multiplier arrangement policy of a kernel instance: every stage single-DSP, or chosen per stage
-enum { KIND_SINGLE = 0, KIND_MIXED = 1 };
+// KIND_SINGLE_PRE (TRUNCATE only): every stage single-DSP AND the twiddles arrive pre-shifted by
+// e = 31 - sh_single (32 - TWDL_WIDTH below 19 bits), so that the multiplier's output slice starts at bit 32 of the
+// 64-bit sum of products: the floor-half a TRUNCATE butterfly consumes is the HIGH WORD of the IMAD.WIDE chain plus
+// one SGXT, instead of a funnel shift + an arithmetic shift (two ALU-port instructions fewer per butterfly, and a
+// shorter dependency chain).  W << e always fits a 32-bit operand: |W| < 2^(TWDL_WIDTH-1).
+enum { KIND_SINGLE = 0, KIND_MIXED = 1, KIND_SINGLE_PRE = 2 };
 
 struct Stg {
     int s, ow, dtwc, kind;
@@ -70,7 +75,7 @@ __device__ __forceinline__ Stg stage_of(const Fast32Params &p, int s)
     const int dtw = p.dw + ii * FORMAT;
     st.ow = dtw + FORMAT;
     st.dtwc = DIT ? dtw : st.ow;
-    st.kind = (KIND == KIND_SINGLE) ? 0 : (st.dtwc < p.cm.lim_single ? 0 : 1);
+    st.kind = (KIND != KIND_MIXED) ? 0 : (st.dtwc < p.cm.lim_single ? 0 : 1);
     // the single arrangement is the double one with no pre-shift: (P2 +- P1) >> sh == ((P2 >> 0) +- (P1 >> 0)) >> sh,
     // so a pass that mixes both runs ONE branch-free code path with per-stage shift amounts
     st.k = st.kind ? p.cm.k_pre : 0;
@@ -126,6 +131,16 @@ __device__ __forceinline__ void cmul32(int dr, int di, int wr, int wi, const Cmu
     }
     const long long tr = (long long)dr * wr - (long long)di * wi;      // 2 x IMAD.WIDE
     const long long ti = (long long)dr * wi + (long long)di * wr;
+    if (KIND == KIND_SINGLE_PRE) {               // MODE_TRUNC; wr / wi carry the factor 2^(31 - sh_single)
+        unsigned rl, rh, il, ih;
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(rl), "=r"(rh) : "l"(tr));
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(il), "=r"(ih) : "l"(ti));
+        o_re.h = sx((int)rh, st.dtwc - 1);       // wrap_dtwc(P >> sh) >> 1 == wrap_(dtwc-1)(P >> (sh + 1))
+        o_im.h = sx((int)ih, st.dtwc - 1);
+        o_re.f = sx((int)__funnelshift_l(rl, rh, 1), st.dtwc);     // only where a consumer needs the full value
+        o_im.f = sx((int)__funnelshift_l(il, ih, 1), st.dtwc);
+        return;
+    }
     const int sh = cm.sh_single;
     o_re.f = field(tr, sh, st.dtwc);
     o_im.f = field(ti, sh, st.dtwc);

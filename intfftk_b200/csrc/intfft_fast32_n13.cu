@@ -263,6 +263,9 @@ template <typename K> cudaError_t launch_n13(K k, const Fast32Params &p, int gri
 template <bool DIT> cudaError_t launch_n13_dir(const Fast32Params &p, int mode, int kind, int klo, int grid, cudaStream_t st)
 {
     constexpr int S = KIND_SINGLE, M = KIND_MIXED;
+    // DIT, TRUNCATE, every stage single-DSP (BASELINE c5): the pre-shifted-twiddle instance; the caller has put the
+    // pre-shifted table / lowest-round twiddles into p (intfft_fast32_strided.cu: launch_fast32)
+    if (DIT && kind == KIND_SINGLE_PRE) return launch_n13(fast32_n13_kernel<DIT, MODE_TRUNC, KIND_SINGLE_PRE, KIND_SINGLE_PRE>, p, grid, st);
     switch (mode * 4 + kind * 2 + klo) {
     case MODE_TRUNC * 4 + 0: return launch_n13(fast32_n13_kernel<DIT, MODE_TRUNC, S, S>, p, grid, st);
     case MODE_TRUNC * 4 + 2: return launch_n13(fast32_n13_kernel<DIT, MODE_TRUNC, M, S>, p, grid, st);
@@ -283,7 +286,7 @@ template <bool DIT> cudaError_t launch_n13_dir(const Fast32Params &p, int mode, 
 int f32_launch_n13(const f32::Fast32Params &p, bool dit, int mode, int kind, int klo, int grid, void *stream)
 {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (klo == f32::KIND_MIXED) kind = f32::KIND_MIXED;     // (single, mixed) is not instantiated: mixed covers it
+    if (klo == f32::KIND_MIXED && kind != f32::KIND_SINGLE_PRE) kind = f32::KIND_MIXED;     // (single, mixed) is not instantiated: mixed covers it
     return (int)(dit ? f32::launch_n13_dir<true>(p, mode, kind, klo, grid, st) : f32::launch_n13_dir<false>(p, mode, kind, klo, grid, st));
 }
 

@@ -1,4 +1,6 @@
 // 32-bit-lane kernels: strided-pass instantiations and the host-side dispatcher (see intfft_fast32.cuh)
+#include <cstdlib>
+
 #include "intfft_fast32.cuh"
 
 namespace intfft {
@@ -19,8 +21,9 @@ bool fast32_supported(const intfft_generics &g)
     return worst <= 32;
 }
 
+// twp / lwp_r / lwp_i: the same twiddles pre-shifted by 31 - sh_single (nullptr when the plan has none)
 int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
-                  int num_sms, void *stream)
+                  int num_sms, void *stream, const int2 *twp, const int *lwp_r, const int *lwp_i)
 {
     f32::Fast32Params p{};
     p.in = pd.kp.in;
@@ -58,6 +61,11 @@ int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const 
         grid = 3ll * num_sms;                          // 80 registers, 70 KB of shared memory: three CTAs per SM
         if (grid > p.n_tiles) grid = p.n_tiles;
         if (grid < 1) grid = 1;
+        if (dit && mode == MODE_TRUNC && kind == f32::KIND_SINGLE && twp && !std::getenv("INTFFT_NO_PRESHIFT")) {
+            p.tw = twp;
+            for (int i = 0; i < 16; ++i) { p.lw_r[i] = lwp_r[i]; p.lw_i[i] = lwp_i[i]; }
+            kind = kind_lo = f32::KIND_SINGLE_PRE;
+        }
         e = f32_launch_n13(p, dit, mode, kind, kind_lo, (int)grid, stream);
     } else if (pd.kp.c == 0) {
         if (grid > p.n_tiles) grid = p.n_tiles;

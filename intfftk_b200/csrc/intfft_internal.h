@@ -91,6 +91,8 @@ struct Plan {
     int2 *d_twp = nullptr;       // twiddles pre-shifted for the 32-bit-product kernel (fast16 plans only)
     int lw_r[16] = {0}, lw_i[16] = {0};  // its lowest-round twiddles (stages 2, 3)
     int lw32_r[16] = {0}, lw32_i[16] = {0};  // same, not pre-shifted (32-bit-lane kernels)
+    int2 *d_twp32 = nullptr;     // twiddles << (31 - sh_single) for the 32-bit-lane TRUNCATE kernels (KIND_SINGLE_PRE)
+    int lwp32_r[16] = {0}, lwp32_i[16] = {0};
     void *scratch[2] = {nullptr, nullptr};
     size_t scratch_bytes[2] = {0, 0};
     // Two-pass plans run group by group: `group_frames` frames go through BOTH passes before the next group
@@ -109,10 +111,14 @@ int launch_tile_pass(const PassDesc &pd, int mode, bool dit, int num_sms, void *
 int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
                   int num_sms, void *stream);
 bool fast16_supported(const intfft_generics &g);
+bool fast16_pair_supported(const intfft_generics &g);
+int launch_fast16_pair(const PassDesc &pd, int mode, const int2 *twp, const int *lw_r, const int *lw_i, int num_sms,
+                       void *stream);
 int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *twp, int num_sms, void *stream);
 bool fast32_supported(const intfft_generics &g);
 int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
-                  int num_sms, void *stream);
+                  int num_sms, void *stream, const int2 *twp = nullptr, const int *lwp_r = nullptr,
+                  const int *lwp_i = nullptr);
 // 64-bit-lane kernel for the lowest eight stage bits (intfft_fast64.cu)
 int fast64_uniform_kind(const PassParams &kp, bool dit);
 int launch_fast64_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw, int num_sms, void *stream);

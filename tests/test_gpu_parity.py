@@ -465,3 +465,125 @@ def test_fft_ifft_pair_roundtrip_full_c2_batch(ib, oracle):
         want = oracle.batch(og, x[f].cpu().numpy()[None])
         assert np.array_equal(y[f].cpu().numpy()[None], want)
     fwd.close(); inv.close()
+
+
+# ---- round 2: ring-staged host pipeline, pair through host buffers, multi-device API, plan re-entrancy ---------------
+@pytest.mark.parametrize("kw,direction,batch", [
+    (dict(NFFT=12, DATA_WIDTH=16, FORMAT=0), 0, 40000),      # 5 chunks of 32 MiB through the 3-slot ring, ragged tail
+    (dict(NFFT=13, DATA_WIDTH=18, FORMAT=0), 1, 2500),       # 64 KiB frames, 512 per chunk
+    (dict(NFFT=16, DATA_WIDTH=24, FORMAT=1), 0, 150),        # two-pass plan, 64-bit output container
+    (dict(NFFT=20, DATA_WIDTH=16, FORMAT=0), 0, 19),         # 4 MiB frames: 8 per chunk
+])
+def test_exec_host_ring_matches_device_path(ib, oracle, kw, direction, batch):
+    """intfft_exec_host streams the batch through a ring of three chunk buffers: every chunk boundary / slot reuse
+    must give what one intfft_exec over the whole batch gives; sampled frames are checked against the oracle."""
+    g = ib.Generics(**kw)
+    n = 1 << g.NFFT
+    core = ib.Core(g, batch, direction)
+    x = core.new_input()
+    ib.fill_random(x, g.DATA_WIDTH, 77)
+    want = core.exec(x).cpu()
+    hx = x.cpu().numpy()
+    got = core.exec_host(hx)
+    assert torch.equal(torch.from_numpy(got), want)
+    xs = 1 if g.XSER == "NEW" else 0
+    og = oracle.generics(g.NFFT, g.DATA_WIDTH, g.TWDL_WIDTH, g.FORMAT, g.RNDMODE, xs, 1, direction)
+    for f in (0, batch // 2, batch - 1):
+        assert np.array_equal(got[f][None], oracle.batch(og, hx[f][None]))
+    core.close()
+
+
+@pytest.mark.parametrize("kw", [dict(NFFT=10, DATA_WIDTH=16, FORMAT=0), dict(NFFT=7, DATA_WIDTH=16, FORMAT=1),
+                                dict(NFFT=13, DATA_WIDTH=14, FORMAT=0, RNDMODE=1)])
+def test_pair_exec_host(ib, oracle, kw):
+    """intfft_pair_exec_host: host buffers in and out, the spectrum stays on the device."""
+    g = ib.Generics(**kw)
+    n, batch = 1 << g.NFFT, 37
+    xs = 1 if g.XSER == "NEW" else 0
+    x = oracle.fill_random(batch * n * 2, g.DATA_WIDTH - 1, 5).reshape(batch, n, 2).astype(oracle.scalar_dtype(g.DATA_WIDTH))
+    mid = oracle.batch(oracle.generics(g.NFFT, g.DATA_WIDTH, g.TWDL_WIDTH, g.FORMAT, g.RNDMODE, xs, 1, 0), x)
+    want = oracle.batch(oracle.generics(g.NFFT, g.out_width, g.TWDL_WIDTH, g.FORMAT, g.RNDMODE, xs, 1, 1), mid)
+    pair = ib.Pair(g, batch)
+    got = pair.exec_host(x)
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+    got2 = pair.exec(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.array_equal(got2, want)
+    pair.close()
+
+
+def test_multi_device_api_one_host_batch(ib, oracle):
+    """intfft_multi_*: one host batch, sharded inside the library over the devices it is given (the same device
+    twice when the box has one GPU: the sharding, the per-device pipelines and their host threads are what is tested)."""
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0, 0]
+    g = ib.Generics(NFFT=12, DATA_WIDTH=16, FORMAT=0)
+    batch = 1001
+    m = ib.Multi(g, batch, 0, devices)
+    sh = m.shards()
+    assert [s[0] for s in sh] == devices
+    assert sh[0][1] == 0 and sum(s[2] for s in sh) == batch
+    assert all(sh[i][1] + sh[i][2] == sh[i + 1][1] for i in range(len(sh) - 1))
+    assert [(s[1], s[1] + s[2]) for s in sh] == [ib.shard_range(batch, i, len(devices)) for i in range(len(devices))]
+    hin = ib.HostBuffer((batch, 4096, 2), np.int16)
+    hout = ib.HostBuffer((batch, 4096, 2), np.int16)
+    hin.array[...] = oracle.fill_random(batch * 4096 * 2, 16, 9).reshape(batch, 4096, 2)
+    m.exec_host_ptr(hin.ptr, hout.ptr)
+    want = oracle.batch(oracle.generics(12), hin.array)
+    assert np.array_equal(hout.array, want)
+    m.close(); hin.close(); hout.close()
+    with pytest.raises(ib.IntfftError):
+        ib.Multi(g, 2, 0, [0, 0, 0])             # fewer frames than devices
+
+
+def test_plan_is_reentrant_on_the_device_path(ib, oracle):
+    """exec entry points no longer write into the plan — exec / exec_natural on ONE plan from several host
+    threads and streams at once must each give their own result."""
+    import threading
+    g = ib.Generics(NFFT=12, DATA_WIDTH=16, FORMAT=0)
+    batch = 4096
+    core = ib.Core(g, batch, 0)
+    x = core.new_input()
+    ib.fill_random(x, 16, 3)
+    want_rev = core.exec(x).clone()
+    want_nat = core.exec_natural(x).clone()
+    torch.cuda.synchronize()
+    assert not torch.equal(want_rev, want_nat)
+    errs = []
+
+    def worker(natural):
+        try:
+            s = torch.cuda.Stream()
+            y = core.new_output()
+            for _ in range(30):
+                (core.exec_natural if natural else core.exec)(x, y, stream=s.cuda_stream)
+                s.synchronize()
+                if not torch.equal(y, want_nat if natural else want_rev):
+                    errs.append(natural)
+                    return
+        except Exception as e:       # pragma: no cover
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(i % 2 == 1,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    core.close()
+
+
+def test_python_mirror_rejects_wrong_tensors(ib):
+    """exec_natural / Pair.exec check device, contiguity, element size and count like exec does."""
+    g = ib.Generics(NFFT=8, DATA_WIDTH=16, FORMAT=0)
+    core = ib.Core(g, 4, 0)
+    x = core.new_input()
+    for bad in (torch.empty((4, 256, 2), dtype=torch.int32, device="cuda"), torch.empty((3, 256, 2), dtype=torch.int16, device="cuda"),
+                torch.empty((4, 256, 2), dtype=torch.int16)):
+        with pytest.raises(ib.IntfftError):
+            core.exec_natural(x, bad)
+        with pytest.raises(ib.IntfftError):
+            core.exec(bad if bad.is_cuda else x, bad)
+    with pytest.raises(ib.IntfftError):
+        core.exec_natural(x, x)
+    pair = ib.Pair(g, 4)
+    with pytest.raises(ib.IntfftError):
+        pair.exec(x, torch.empty((4, 256, 2), dtype=torch.int32, device="cuda"))
+    pair.close(); core.close()
