@@ -203,6 +203,13 @@ int upload_twiddles(Plan &pl)
             }
         if (cudaMalloc(&pl.d_twp32, cnt * sizeof(int2)) != cudaSuccess) return INTFFT_ENOMEM;
         if (cudaMemcpy(pl.d_twp32, tp.data(), cnt * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) return INTFFT_ECUDA;
+        if (n == 13 && pl.g.twdl_width <= 16) {        // STAGE 12 of the one-pass 8192-point kernel, 4 bytes per twiddle
+            std::vector<unsigned> pk(4096);
+            for (size_t k = 0; k < 4096; ++k)
+                pk[k] = ((unsigned)tab[4096 + k].x << 16) | ((unsigned)tab[4096 + k].y & 0xffffu);
+            if (cudaMalloc(&pl.d_tw12p, pk.size() * sizeof(unsigned)) != cudaSuccess) return INTFFT_ENOMEM;
+            if (cudaMemcpy(pl.d_tw12p, pk.data(), pk.size() * sizeof(unsigned), cudaMemcpyHostToDevice) != cudaSuccess) return INTFFT_ECUDA;
+        }
     }
     if (!pl.passes.empty() && pl.passes[0].path == 1) {
         // 32-bit-product kernel: W << e with e = 33 - TWDL_WIDTH - DATA_WIDTH puts the multiplier's
@@ -320,6 +327,7 @@ int intfft_plan_destroy(intfft_plan *p)
     cudaFree(p->d_tw);
     cudaFree(p->d_twp);
     cudaFree(p->d_twp32);
+    cudaFree(p->d_tw12p);
     cudaFree(p->scratch[0]);
     cudaFree(p->scratch[1]);
     cudaFree(p->nat);
@@ -366,7 +374,7 @@ static int run_pass(const intfft_plan *p, size_t i, const void *in, void *out, l
                         : launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream);
     else if (pd.path == 2)
         e = launch_fast32(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream, p->d_twp32,
-                          p->lwp32_r, p->lwp32_i);
+                          p->lwp32_r, p->lwp32_i, p->d_tw12p);
     else if (pd.path == 3)
         e = launch_fast64(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
     else if (pd.path == 4)

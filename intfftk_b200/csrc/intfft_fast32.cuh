@@ -26,6 +26,7 @@ struct Fast32Params {
     const void *in;
     void *out;
     const int2 *tw;          // raw twiddles, entry (1 << s) + k
+    const unsigned *tw16;    // KIND_SINGLE_PRE: STAGE-12 twiddles packed {re:16 | im:16} (TWDL_WIDTH <= 16), entry k
     long long n_tiles;       // contiguous: tiles of 4096 samples
     long long total;         // frames * N
     long long batch;
@@ -697,6 +698,9 @@ template <typename K> cudaError_t launch_any(K k, const Fast32Params &p, int gri
 // one translation unit per direction keeps the build parallel
 template <int NLOG2, bool DIT> cudaError_t launch_contig(const Fast32Params &p, int mode, int kind, int grid, cudaStream_t st)
 {
+    if constexpr (DIT) {         // TRUNCATE, every stage single-DSP, pre-shifted twiddles in p (launch_fast32)
+        if (kind == KIND_SINGLE_PRE) return launch_any(fast32_kernel<NLOG2, DIT, MODE_TRUNC, KIND_SINGLE_PRE>, p, grid, st);
+    }
     switch (mode * 2 + kind) {
     case MODE_TRUNC * 2 + 0: return launch_any(fast32_kernel<NLOG2, DIT, MODE_TRUNC, KIND_SINGLE>, p, grid, st);
     case MODE_TRUNC * 2 + 1: return launch_any(fast32_kernel<NLOG2, DIT, MODE_TRUNC, KIND_MIXED>, p, grid, st);
@@ -724,6 +728,9 @@ template <bool DIT> cudaError_t launch_contig_n(const Fast32Params &p, int bits,
 }
 template <int G, bool DIT> cudaError_t launch_strided(const Fast32Params &p, int mode, int kind, int grid, cudaStream_t st)
 {
+    if constexpr (DIT) {
+        if (kind == KIND_SINGLE_PRE) return launch_any(fast32_strided_kernel<G, DIT, MODE_TRUNC, KIND_SINGLE_PRE>, p, grid, st);
+    }
     switch (mode * 2 + kind) {
     case MODE_TRUNC * 2 + 0: return launch_any(fast32_strided_kernel<G, DIT, MODE_TRUNC, KIND_SINGLE>, p, grid, st);
     case MODE_TRUNC * 2 + 1: return launch_any(fast32_strided_kernel<G, DIT, MODE_TRUNC, KIND_MIXED>, p, grid, st);

@@ -72,6 +72,16 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
 #pragma unroll
     for (int i = 0; i < 15; ++i) { lwr[i] = p.lw_r[i]; lwi[i] = p.lw_i[i]; }
     const int2 *twD = p.tw + (1u << 12) + tid;         // STAGE 12: index tid + 256 m (read through L1 / L2 per frame)
+    // KIND_SINGLE_PRE: the same 4096 twiddles packed into 16 KB, which stays resident in the 28 KB of L1 that three
+    // 74 KB CTAs leave (the 32 KB int2 table does not: every frame fetched it from L2 again, 8 % long-scoreboard stalls)
+    const unsigned *twP = p.tw16 + tid;
+    auto tw12 = [&](int m) {
+        if (KIND == KIND_SINGLE_PRE) {
+            const unsigned x = __ldg(twP + 256 * m);
+            return make_int2((int)(x & 0xffff0000u), (int)(x << 16));       // re << 16, im << 16: already pre-shifted
+        }
+        return __ldg(twD + 256 * m);
+    };
     __syncthreads();
 
     const unsigned pA = pA_of(tid);
@@ -115,7 +125,7 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
                 int ar, ai, br, bi;
                 ld_sample(p.in, g0 + tid + 256u * m, p.in_sb, ar, ai);
                 ld_sample(p.in, g0 + 4096 + tid + 256u * m, p.in_sb, br, bi);
-                const int2 w = __ldg(twD + 256 * m);
+                const int2 w = tw12(m);
                 V xr = mk(sx(ar, p.dw)), xi = mk(sx(ai, p.dw)), yr = mk(sx(br, p.dw)), yi = mk(sx(bi, p.dw));
                 fly32<DIT, MODE, KIND>(stD, false, p.cm, xr, xi, yr, yi, w.x, w.y);
                 re[m] = xr;
@@ -192,7 +202,7 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int m = 2 * j + e;
-                        const int2 w = __ldg(twD + 256 * m);
+                        const int2 w = tw12(m);
                         V xr = mk(e ? a.z : a.x), xi = mk(e ? a.w : a.y);
                         fly32<DIT, MODE, KIND>(stD, false, p.cm, xr, xi, re[m], im[m], w.x, w.y);
                         st_sample(p.out, g0 + tid + 256u * m, OSB, xr.f, xi.f);

@@ -93,6 +93,7 @@ struct Plan {
     int lw32_r[16] = {0}, lw32_i[16] = {0};  // same, not pre-shifted (32-bit-lane kernels)
     int2 *d_twp32 = nullptr;     // twiddles << (31 - sh_single) for the 32-bit-lane TRUNCATE kernels (KIND_SINGLE_PRE)
     int lwp32_r[16] = {0}, lwp32_i[16] = {0};
+    unsigned *d_tw12p = nullptr; // STAGE-12 twiddles packed {re:16 | im:16} (one-pass 8192-point kernel, TWDL_WIDTH <= 16)
     void *scratch[2] = {nullptr, nullptr};
     size_t scratch_bytes[2] = {0, 0};
     // Two-pass plans run group by group: `group_frames` frames go through BOTH passes before the next group
@@ -118,7 +119,7 @@ int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw
 bool fast32_supported(const intfft_generics &g);
 int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
                   int num_sms, void *stream, const int2 *twp = nullptr, const int *lwp_r = nullptr,
-                  const int *lwp_i = nullptr);
+                  const int *lwp_i = nullptr, const unsigned *tw16 = nullptr);
 // 64-bit-lane kernel for the lowest eight stage bits (intfft_fast64.cu)
 int fast64_uniform_kind(const PassParams &kp, bool dit);
 int launch_fast64_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw, int num_sms, void *stream);
