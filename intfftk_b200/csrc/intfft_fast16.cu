@@ -520,6 +520,230 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
+// One-pass 8192-point packed-16 kernel (NFFT = 13, 16-bit scaled): replaces the strided-4 + contiguous-9 two-pass
+// schedule, so every sample is read from HBM once and written once and one of the two load / exchange / store
+// sequences disappears.  A 256-thread CTA owns a frame and walks its two 4096-sample blocks with the three
+// register rounds of fast16_kernel<12>; STAGE 12 pairs sample i of the lower block with sample i of the upper one,
+// and in the top round's ownership (tid + 256 m) both belong to the SAME thread, so that stage needs no exchange:
+//   DIF: the frame lands as ONE 32 KB TMA bulk copy; STAGE 12 runs straight out of the landing buffer — the sums
+//        stay in registers as the lower block's top-round input, the products go back into the thread's own slots
+//        of the upper half of the landing buffer, which the upper block then reads like any TMA-landed tile.  The
+//        next frame's copy is issued once every thread has read those slots (single-buffered, hidden behind the
+//        upper block's last two rounds and the two other CTAs of the SM).
+//   DIT: the lower block's top-round results wait in thread-private slots of the second exchange tile while the
+//        upper block is computed, then STAGE 12 runs between those slots and the registers and both halves of the
+//        frame leave as warp-coalesced 128-byte stores.  Blocks land per warp with cp.async, one block ahead.
+// Same arithmetic (fly<>, round_regs<>) and twiddle placement as fast16_kernel; STAGE-12 twiddles are read through
+// L1 / L2 per frame (16 per thread).
+template <bool DIT, bool DW16, int MODE>
+__global__ void __launch_bounds__(256, 3) fast16_n13_kernel(const __grid_constant__ Fast16Params p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);
+    uint32_t(*work)[kTileWords] = reinterpret_cast<uint32_t(*)[kTileWords]>(smem_raw + kSmemHead);
+    uint32_t(*stage)[4096] = reinterpret_cast<uint32_t(*)[4096]>(smem_raw + kSmemHead + 2 * kTileWords * 4);   // DIF
+    uint32_t *land = reinterpret_cast<uint32_t *>(smem_raw + kSmemHead + 2 * kTileWords * 4);                    // DIT
+
+    const unsigned tid = threadIdx.x;
+    const int sh_full = p.sh_full, sh_half = p.sh_half;
+    const bool tid_odd = tid & 1u;
+    const long long n_frames = p.n_tiles;            // frames of 8192 samples
+    constexpr bool RAW = !DIT && DW16;
+    auto warp_piece = [&](int c) {                   // 16-byte piece lane + 32 c of the warp's 512 contiguous samples
+        const unsigned q = (tid & 31u) + 32u * c;
+        return ((tid & ~31u) << 4) + 4u * q;
+    };
+
+    if (!DIT) {
+        if (tid == 0) {
+            mbar_init(&bar[0], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0 && (long long)blockIdx.x < n_frames) {
+            mbar_expect_tx(&bar[0], 32768u);
+            tma_load_1d(stage[0], p.in + ((long long)blockIdx.x << 13), 32768u, &bar[0]);
+        }
+    }
+    auto prefetch_warp = [&](long long block) {      // DIT: one 4096-sample block -> the skewed landing tile
+        const long long g = block << 12;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned i = warp_piece(j);
+            cp_async_16z(land + phys(i), p.in + g + i, 16u);
+        }
+        cp_async_commit_group();
+    };
+    if (DIT && (long long)blockIdx.x < n_frames) prefetch_warp((long long)blockIdx.x << 1);
+
+    // ---- batch-invariant twiddles: STAGE 4..7 table, STAGE 8..11 registers, STAGE 2..3 parameters ----
+    if (tid < 240) {
+        const int w = tid >> 4, lo4 = tid & 15;
+        const int q = w >= 7 ? 3 : (w >= 3 ? 2 : (w >= 1 ? 1 : 0));
+        const int j = w - ((1 << q) - 1);
+        midtw[w * 16 + lo4] = __ldg(p.twp + (1u << (4 + q)) + lo4 + ((unsigned)j << 4));
+    }
+    int uwr[15], uwi[15];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < (1 << q); ++j) {
+            const int2 w = __ldg(p.twp + (1u << (8 + q)) + tid + ((unsigned)j << 8));
+            uwr[(1 << q) - 1 + j] = w.x;
+            uwi[(1 << q) - 1 + j] = w.y;
+        }
+    int lwr[15], lwi[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) { lwr[i] = p.lw_r[i]; lwi[i] = p.lw_i[i]; }
+    const int2 *tw12 = p.twp + 4096 + tid;           // STAGE 12: index tid + 256 m
+    __syncthreads();
+
+    const unsigned pA = phys(16u * tid);                                    // round 0: 16 contiguous samples
+    const unsigned pB = phys((tid & 15u) | ((tid >> 4) << 8));              // round 1: stride 16
+    const unsigned pC = phys(tid);                                          // round 2: stride 256
+
+    int it = 0;
+    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++it) {
+        const long long g0 = frame << 13;
+        int re[16], im[16];
+
+        if (!DIT) {
+            // ---- STAGE 12 out of the landing buffer: sums -> registers, products -> the thread's own upper slots ----
+            mbar_wait(&bar[0], it & 1);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                int br, bi;
+                unpack<DW16>(stage[0][tid + 256 * m], p.dw, re[m], im[m]);
+                unpack<DW16>(stage[1][tid + 256 * m], p.dw, br, bi);
+                const int2 w = __ldg(tw12 + 256 * m);
+                fly<false, DW16, MODE, RAW>(12, false, re[m], im[m], br, bi, w.x, w.y, sh_full, sh_half);
+                stage[1][tid + 256 * m] = RAW ? __byte_perm((unsigned)br, (unsigned)bi, 0x7632) : pack(br, bi);
+            }
+#pragma unroll 1
+            for (int blk = 0; blk < 2; ++blk) {
+                uint32_t *sm = work[blk];
+                if (blk) {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) unpack<true>(stage[1][tid + 256 * m], p.dw, re[m], im[m]);
+                }
+                // round 2: STAGE 11..8 (stride 256)
+                round_regs<8, 4, false, DW16, MODE, RAW>(re, im, TwRegs{uwr, uwi}, tid_odd, sh_full, sh_half);
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+                    sm[pC + phys((unsigned)m << 8)] = (RAW && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632) : pack(re[m], im[m]);
+                __syncthreads();
+                // every thread has read the landing buffer (its STAGE-12 operands and, in the upper block, its own
+                // product slots): the next frame may land
+                if (blk == 1 && tid == 0 && frame + gridDim.x < n_frames) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic stores -> TMA writes
+                    mbar_expect_tx(&bar[0], 32768u);
+                    tma_load_1d(stage[0], p.in + ((frame + gridDim.x) << 13), 32768u, &bar[0]);
+                }
+                // round 1: STAGE 7..4 (stride 16)
+#pragma unroll
+                for (int m = 0; m < 16; ++m) unpack<true>(sm[pB + phys((unsigned)m << 4)], p.dw, re[m], im[m]);
+                round_regs<4, 4, false, DW16, MODE, RAW>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+                    sm[pB + phys((unsigned)m << 4)] = (RAW && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632) : pack(re[m], im[m]);
+                __syncwarp();                                   // this hand-over stays inside the warp
+                // round 0: STAGE 3..0 (16 contiguous samples)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(sm + pA + phys(4 * c));
+                    unpack<true>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
+                    unpack<true>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
+                    unpack<true>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
+                    unpack<true>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                }
+                round_regs<0, 4, false, DW16, MODE, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4 *>(sm + pA + phys(4 * c)) =
+                        make_uint4(pack(re[4 * c], im[4 * c]), pack(re[4 * c + 1], im[4 * c + 1]),
+                                   pack(re[4 * c + 2], im[4 * c + 2]), pack(re[4 * c + 3], im[4 * c + 3]));
+                __syncwarp();
+                uint32_t *dst = p.out + g0 + 4096 * blk;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const unsigned i = warp_piece(c);
+                    *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(sm + phys(i));
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int blk = 0; blk < 2; ++blk) {
+                uint32_t *sm = work[0];
+                // round 0: STAGE 0..3 on the block the warp landed one block ago
+                cp_async_wait_group0();
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(land + pA + phys(4 * c));
+                    unpack<DW16>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
+                    unpack<DW16>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
+                    unpack<DW16>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
+                    unpack<DW16>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                }
+                __syncwarp();                                   // every lane has drained the warp's region
+                {
+                    const long long nb = blk == 0 ? 2 * frame + 1 : 2 * (frame + gridDim.x);
+                    if (nb < 2 * n_frames) prefetch_warp(nb);
+                }
+                round_regs<0, 4, true, DW16, MODE, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
+                // the exchange tile is single (the second one parks the lower block): the previous block's cross-warp
+                // reads of it must be complete before this block writes
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4 *>(sm + pA + phys(4 * c)) =
+                        make_uint4(pack(re[4 * c], im[4 * c]), pack(re[4 * c + 1], im[4 * c + 1]),
+                                   pack(re[4 * c + 2], im[4 * c + 2]), pack(re[4 * c + 3], im[4 * c + 3]));
+                __syncwarp();
+                // round 1: STAGE 4..7
+#pragma unroll
+                for (int m = 0; m < 16; ++m) unpack<true>(sm[pB + phys((unsigned)m << 4)], p.dw, re[m], im[m]);
+                round_regs<4, 4, true, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) sm[pB + phys((unsigned)m << 4)] = pack(re[m], im[m]);
+                __syncthreads();
+                // round 2: STAGE 8..11
+#pragma unroll
+                for (int m = 0; m < 16; ++m) unpack<true>(sm[pC + phys((unsigned)m << 8)], p.dw, re[m], im[m]);
+                round_regs<8, 4, true, DW16, MODE, false>(re, im, TwRegs{uwr, uwi}, tid_odd, sh_full, sh_half);
+                if (blk == 0) {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) work[1][m * 256 + tid] = pack(re[m], im[m]);     // thread-private slots
+                } else {
+                    // ---- STAGE 12 between the parked lower block and the registers; both halves leave coalesced ----
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        int ar, ai;
+                        unpack<true>(work[1][m * 256 + tid], p.dw, ar, ai);
+                        const int2 w = __ldg(tw12 + 256 * m);
+                        fly<true, DW16, MODE>(12, false, ar, ai, re[m], im[m], w.x, w.y, sh_full, sh_half);
+                        p.out[g0 + tid + 256 * m] = pack(ar, ai);
+                        p.out[g0 + 4096 + tid + 256 * m] = pack(re[m], im[m]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <bool DIT, bool DW16>
+cudaError_t launch_n13_k(const Fast16Params &p, int mode, int grid, cudaStream_t st)
+{
+    const int smem = kSmemHead + 2 * kTileWords * 4 + (DIT ? (int)kTileWords * 4 : 2 * 4096 * 4);
+    auto k = mode == MODE_ROUND ? fast16_n13_kernel<DIT, DW16, MODE_ROUND> : fast16_n13_kernel<DIT, DW16, MODE_TRUNC>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Strided pass for NFFT = 13..20 (16-bit scaled TRUNCATE): the top G = 4 or 8 stage bits of a frame.
 // A tile is 2^G rows (stride 2^(NFFT-G) samples) by 2^(12-G) contiguous columns; a CTA keeps one
 // column block ("mid") and walks over frames, so the between-pass twiddles — which depend on the
@@ -780,6 +1004,32 @@ int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const
         break;
     default: e = cudaErrorInvalidValue; break;
     }
+    count_launch();
+    return (int)e;
+}
+
+// one-pass 8192-point packed-16 plan (kp.g == 13)
+int launch_fast16_n13(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
+                      int num_sms, void *stream)
+{
+    Fast16Params p{};
+    p.in = reinterpret_cast<const uint32_t *>(pd.kp.in);
+    p.out = reinterpret_cast<uint32_t *>(pd.kp.out);
+    p.twp = twp;
+    p.total = pd.kp.total;
+    p.n_tiles = pd.kp.total >> 13;                  // frames
+    p.dw = pd.kp.dw;
+    p.sh_full = 32 - p.dw;
+    p.sh_half = 33 - p.dw;
+    for (int i = 0; i < 16; ++i) { p.lw_r[i] = lw_r[i]; p.lw_i[i] = lw_i[i]; }
+    long long grid = 3ll * num_sms;
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    if (grid < 1) grid = 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool dw16 = p.dw == 16;
+    cudaError_t e;
+    if (!dit) e = dw16 ? launch_n13_k<false, true>(p, mode, (int)grid, st) : launch_n13_k<false, false>(p, mode, (int)grid, st);
+    else e = dw16 ? launch_n13_k<true, true>(p, mode, (int)grid, st) : launch_n13_k<true, false>(p, mode, (int)grid, st);
     count_launch();
     return (int)e;
 }
