@@ -116,6 +116,11 @@ int intfft_host_free(void *h_ptr);
 /* Twiddle read-back: the W(k), k = 0 .. 2^stage - 1, that rom_twiddle_int(STAGE = stage) streams
  * (rom_twiddle_int.vhd:98-248); stage >= 2.  Host-only, needs no device. */
 int intfft_twiddles(const intfft_generics *g, int stage, int32_t *h_re, int32_t *h_im);
+/* Test hook for the on-device Taylor path (strided kernels of NFFT >= 17 plans recompute their STAGE >= 11
+ * twiddles from the 512-entry coarse ROM instead of reading 2^NFFT-entry tables): the same device function,
+ * evaluated for every k of `stage` (11..19) on `device`.  Must equal intfft_twiddles bit for bit.
+ * Replaces: rom_twiddle_int.vhd:215-246 + row_twiddle_tay.vhd:123-382 as they run in hardware (per sample). */
+int intfft_twiddles_device(const intfft_generics *g, int stage, int32_t *h_re, int32_t *h_im, int device);
 
 /* f2: the FFT -> IFFT loop-back of int_fft_ifft_pair (main/int_fft_ifft_pair.vhd:209-283):
  * int_fftNk(generics) feeding int_ifftNk with DATA_WIDTH + FORMAT*NFFT input bits (:261), natural order in,

@@ -5,8 +5,8 @@ Host-side mirror of the reference interface: the entity generics of `int_fftNk` 
 becomes a `Core` bound to the C-ABI in include/intfft.h.  PyTorch is used only for device memory and
 streams.  There is no CPU fallback: importing `core` loads libintfft_b200.so or raises.
 """
-from .core import (Core, Pair, Multi, HostBuffer, Generics, IntfftError, int_fftNk, int_ifftNk, set_mode, lib, twiddles, validate,
+from .core import (Core, Pair, Multi, HostBuffer, Generics, IntfftError, int_fftNk, int_ifftNk, set_mode, lib, twiddles, twiddles_device, validate,
                    bitrev_order, fill_random, checksum, launch_count, shard_range, describe)
 
-__all__ = ["Core", "Pair", "Multi", "HostBuffer", "Generics", "IntfftError", "int_fftNk", "int_ifftNk", "set_mode", "lib", "twiddles",
+__all__ = ["Core", "Pair", "Multi", "HostBuffer", "Generics", "IntfftError", "int_fftNk", "int_ifftNk", "set_mode", "lib", "twiddles", "twiddles_device",
            "validate", "bitrev_order", "fill_random", "checksum", "launch_count", "shard_range", "describe"]

@@ -57,6 +57,7 @@ def lib() -> ctypes.CDLL:
         L.intfft_exec_host.argtypes = [vp, vp, vp]
         L.intfft_exec_natural.argtypes = [vp, vp, vp, vp]
         L.intfft_twiddles.argtypes = [P(_CGenerics), ctypes.c_int, vp, vp]
+        L.intfft_twiddles_device.argtypes = [P(_CGenerics), ctypes.c_int, vp, vp, ctypes.c_int]
         L.intfft_pair_create.argtypes = [P(vp), P(_CGenerics), ctypes.c_int, ctypes.c_int64, ctypes.c_int]
         L.intfft_pair_destroy.argtypes = [vp]
         L.intfft_pair_query.argtypes = [vp, P(_CLayout)]
@@ -144,6 +145,17 @@ def twiddles(g: Generics, stage: int):
     st = lib().intfft_twiddles(ctypes.byref(c), stage, re.ctypes.data, im.ctypes.data)
     if st:
         raise IntfftError(st, "intfft_twiddles")
+    return re, im
+
+
+def twiddles_device(g: Generics, stage: int, device: int = 0):
+    """The same stream recomputed by the kernels' on-device Taylor function (STAGE 11..19; needs a GPU)."""
+    c = g.c_struct(0)
+    re = np.empty(1 << stage, np.int32)
+    im = np.empty(1 << stage, np.int32)
+    st = lib().intfft_twiddles_device(ctypes.byref(c), stage, re.ctypes.data, im.ctypes.data, device)
+    if st:
+        raise IntfftError(st, "intfft_twiddles_device")
     return re, im
 
 

@@ -168,13 +168,42 @@ void build_passes(Plan &pl)
     }
 }
 
+// N > 64K on the strided kernels: STAGE >= 11 twiddles of the strided pass are recomputed on the device (coarse ROM +
+// Taylor MACs, intfft_taylor.cuh) where the kernel hoists them, so the tables stop at STAGE 11 (2^12 entries instead
+// of 2^NFFT: 32 KB instead of 8 MB per table at NFFT = 20) and plan creation skips the host-side Taylor sweep.
+// INTFFT_TAYLOR_MIN_NFFT moves the threshold (13 = every two-pass plan on those kernels, 99 = tables only).
+static bool wants_device_taylor(const Plan &pl)
+{
+    int min_nfft = 17;
+    if (const char *e = std::getenv("INTFFT_TAYLOR_MIN_NFFT")) min_nfft = std::atoi(e);
+    if (pl.g.nfft_log2 < min_nfft || pl.g.nfft_log2 < 13 || pl.passes.size() != 2) return false;
+    for (const PassDesc &pd : pl.passes) {
+        if (pd.path != 1 && pd.path != 2) return false;                   // packed-16 / 32-bit-lane kernels only
+        if (pd.kp.c == 0 && pd.kp.g > 12) return false;                   // contiguous pass reads STAGE < 12 tables
+    }
+    return true;
+}
+
 int upload_twiddles(Plan &pl)
 {
     const int n = pl.g.nfft_log2;
-    const size_t cnt = (size_t)1 << n;
+    const bool tay = wants_device_taylor(pl);
+    const size_t cnt = (size_t)1 << (tay ? 12 : n);
+    if (tay) {
+        std::vector<int32_t> rc(512), rs(512);
+        taylor_consts(pl.g.twdl_width, pl.g.xser, rc.data(), rs.data(), pl.tay.mathpi, &pl.tay.xs);
+        std::vector<int2> rom(512);
+        for (int i = 0; i < 512; ++i) rom[i] = make_int2(rc[i], rs[i]);
+        if (cudaMalloc(&pl.d_rom9, 512 * sizeof(int2)) != cudaSuccess) return INTFFT_ENOMEM;
+        if (cudaMemcpy(pl.d_rom9, rom.data(), 512 * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) return INTFFT_ECUDA;
+        pl.tay.rom9 = pl.d_rom9;
+        pl.tay.tw = pl.g.twdl_width;
+        pl.tay.e = 0;
+        pl.tay.on = 1;
+    }
     std::vector<int2> tab(cnt, make_int2(0, 0));
     std::vector<int32_t> re(cnt / 2), im(cnt / 2);
-    for (int s = 2; s < n; ++s) {
+    for (int s = 2; s < n && ((size_t)2 << s) <= cnt; ++s) {
         twiddle_stage_table(s, pl.g.twdl_width, pl.g.xser, re.data(), im.data());
         for (size_t k = 0; k < ((size_t)1 << s); ++k) tab[((size_t)1 << s) + k] = make_int2(re[k], im[k]);
     }
@@ -203,7 +232,7 @@ int upload_twiddles(Plan &pl)
             }
         if (cudaMalloc(&pl.d_twp32, cnt * sizeof(int2)) != cudaSuccess) return INTFFT_ENOMEM;
         if (cudaMemcpy(pl.d_twp32, tp.data(), cnt * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) return INTFFT_ECUDA;
-        if (n == 13 && pl.g.twdl_width <= 16) {        // STAGE 12 of the one-pass 8192-point kernel, 4 bytes per twiddle
+        if (n == 13 && !tay && pl.g.twdl_width <= 16) {        // STAGE 12 of the one-pass 8192-point kernel, 4 bytes per twiddle
             std::vector<unsigned> pk(4096);
             for (size_t k = 0; k < 4096; ++k)
                 pk[k] = ((unsigned)tab[4096 + k].x << 16) | ((unsigned)tab[4096 + k].y & 0xffffu);
@@ -215,6 +244,8 @@ int upload_twiddles(Plan &pl)
         // 32-bit-product kernel: W << e with e = 33 - TWDL_WIDTH - DATA_WIDTH puts the multiplier's
         // output slice P(DTW+TWD-2 downto TWD-1) (int_cmult_dsp48.vhd:189-190) at bits 31 .. 32-DTW
         const int e = 33 - pl.g.twdl_width - pl.g.data_width;
+        pl.tay16 = pl.tay;
+        pl.tay16.e = e;
         std::vector<int2> tp(cnt);
         for (size_t i = 0; i < cnt; ++i) tp[i] = make_int2(tab[i].x * (1 << e), tab[i].y * (1 << e));
         for (int s = 2; s <= 3 && s < n; ++s)
@@ -328,6 +359,7 @@ int intfft_plan_destroy(intfft_plan *p)
     cudaFree(p->d_twp);
     cudaFree(p->d_twp32);
     cudaFree(p->d_tw12p);
+    cudaFree(p->d_rom9);
     cudaFree(p->scratch[0]);
     cudaFree(p->scratch[1]);
     cudaFree(p->nat);
@@ -370,12 +402,12 @@ static int run_pass(const intfft_plan *p, size_t i, const void *in, void *out, l
     pd.natural = natural;
     int e;
     if (pd.path == 1)
-        e = pd.kp.c > 0 ? launch_fast16_strided(pd, p->mode, dit, p->d_twp, p->num_sms, cuda_stream)
+        e = pd.kp.c > 0 ? launch_fast16_strided(pd, p->mode, dit, p->d_twp, p->num_sms, cuda_stream, &p->tay16)
             : (pd.kp.g == 13 ? launch_fast16_n13(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream)
                              : launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream));
     else if (pd.path == 2)
         e = launch_fast32(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream, p->d_twp32,
-                          p->lwp32_r, p->lwp32_i, p->d_tw12p);
+                          p->lwp32_r, p->lwp32_i, p->d_tw12p, &p->tay);
     else if (pd.path == 3)
         e = launch_fast64(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream);
     else if (pd.path == 4)
@@ -762,6 +794,37 @@ int intfft_twiddles(const intfft_generics *g, int stage, int32_t *h_re, int32_t 
     if (!g || !h_re || !h_im || stage < 2 || stage > 19) return INTFFT_EINVAL;
     if (g->twdl_width < 8 || g->twdl_width > ((g->xser & 1) ? 27 : 25)) return INTFFT_EINVAL;
     twiddle_stage_table(stage, g->twdl_width, g->xser & 1, h_re, h_im);
+    return INTFFT_OK;
+}
+
+// Test hook for the on-device Taylor path: the kernels' own device function evaluated for every k of the stage
+int intfft_twiddles_device(const intfft_generics *g, int stage, int32_t *h_re, int32_t *h_im, int device)
+{
+    if (!g || !h_re || !h_im || stage < 11 || stage > 19) return INTFFT_EINVAL;
+    if (g->twdl_width < 8 || g->twdl_width > ((g->xser & 1) ? 27 : 25)) return INTFFT_EINVAL;
+    DeviceGuard guard(device);
+    if (!guard.ok) return INTFFT_ECUDA;
+    std::vector<int32_t> rc(512), rs(512);
+    TaylorDev t{};
+    taylor_consts(g->twdl_width, g->xser & 1, rc.data(), rs.data(), t.mathpi, &t.xs);
+    std::vector<int2> rom(512);
+    for (int i = 0; i < 512; ++i) rom[i] = make_int2(rc[i], rs[i]);
+    const size_t cnt = (size_t)1 << stage;
+    int2 *d_rom = nullptr, *d_out = nullptr;
+    int st = INTFFT_OK;
+    if (cudaMalloc(&d_rom, 512 * sizeof(int2)) != cudaSuccess || cudaMalloc(&d_out, cnt * sizeof(int2)) != cudaSuccess) st = INTFFT_ENOMEM;
+    std::vector<int2> out(cnt);
+    if (st == INTFFT_OK) {
+        t.rom9 = d_rom; t.tw = g->twdl_width; t.e = 0; t.on = 1;
+        if (cudaMemcpy(d_rom, rom.data(), 512 * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess ||
+            launch_taylor_table(t, stage, d_out, nullptr) != 0 ||
+            cudaMemcpy(out.data(), d_out, cnt * sizeof(int2), cudaMemcpyDeviceToHost) != cudaSuccess)
+            st = INTFFT_ECUDA;
+    }
+    cudaFree(d_rom);
+    cudaFree(d_out);
+    if (st != INTFFT_OK) return st;
+    for (size_t k = 0; k < cnt; ++k) { h_re[k] = out[k].x; h_im[k] = out[k].y; }
     return INTFFT_OK;
 }
 

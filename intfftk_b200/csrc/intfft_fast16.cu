@@ -24,9 +24,12 @@
 //     pattern (32-bit at stride 256 / 16, 128-bit contiguous) is bank-conflict free for N = 4096.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <type_traits>
+#include <vector>
 
 #include "intfft_internal.h"
+#include "intfft_taylor.cuh"
 
 namespace intfft {
 
@@ -759,6 +762,7 @@ struct Strided16Params {
     int frames_per_unit;
     long long n_units;      // mid_count * ceil(batch / frames_per_unit)
     int dw, sh_full, sh_half;
+    TaylorDev tay;          // .on: STAGE >= 11 twiddles are recomputed here (rom9 + Taylor MACs), twp ends at STAGE 11
 };
 
 // Shared memory of the strided pass: [head | exchange tile | 2 x landing tile]; all three tiles use the
@@ -796,9 +800,14 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
     const int sh_full = p.sh_full, sh_half = p.sh_half;
     const int pb = p.n - G;                         // lowest global bit of this pass
     const unsigned cmask = (1u << C) - 1u;
-    const int mid_bits = pb - C;
 
     int it = 0;
+    // Units = (frame chunk, column block), column block fastest, dealt round-robin: the CTAs running at any moment
+    // cover ALL column blocks of the same few frames, so the 64-byte row pieces of neighbouring blocks — two to a
+    // 128-byte line — are fetched together and the frames stream through DRAM page by page.  (Giving every CTA one
+    // contiguous range of (block, frame) items instead balances the load perfectly but loses that locality:
+    // c4 1.27 -> 1.59 ms, measured r02.)  The launcher picks the chunk length that balances the round-robin deal.
+    const int mid_bits = pb - C;
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const unsigned mid = (unsigned)(u & ((1ll << mid_bits) - 1));
         const long long f0 = (u >> mid_bits) * p.frames_per_unit;
@@ -830,7 +839,7 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < (1 << q); ++j) {
                 const int sgl = pb + (8 + q - C);
-                const int2 w = __ldg(p.twp + (1u << sgl) + (kidx(tid | ((unsigned)j << 8)) & ((1u << sgl) - 1u)));
+                const int2 w = hoist_twiddle(p.twp, p.tay, sgl, kidx(tid | ((unsigned)j << 8)) & ((1u << sgl) - 1u));
                 uwr[(1 << q) - 1 + j] = w.x;
                 uwi[(1 << q) - 1 + j] = w.y;
             }
@@ -841,7 +850,7 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
                 const int q = w >= 7 ? 3 : (w >= 3 ? 2 : (w >= 1 ? 1 : 0));
                 const int j = w - ((1 << q) - 1);
                 const int sgl = pb + (4 + q - C);
-                midtw[w * 16 + lo4] = __ldg(p.twp + (1u << sgl) + (kidx((unsigned)lo4 | ((unsigned)j << 4)) & ((1u << sgl) - 1u)));
+                midtw[w * 16 + lo4] = hoist_twiddle(p.twp, p.tay, sgl, kidx((unsigned)lo4 | ((unsigned)j << 4)) & ((1u << sgl) - 1u));
             }
         }
 
@@ -930,10 +939,47 @@ bool fast16_supported(const intfft_generics &g)
            g.nfft_log2 >= 3 && g.nfft_log2 <= 20;
 }
 
+// Chunk length of the strided pass's round-robin deal.  Unit u = (chunk u / mids, column block u % mids) goes to
+// CTA u % grid; a unit costs its frames plus `hoist` frame-times for fetching / recomputing the block's twiddles.
+// Picks the length whose most loaded CTA finishes first (c4: 12 chunks of 22 frames = 6.9 waves instead of the old
+// fixed "8 x grid units" rule's 14 chunks of 19 = 8.07 waves, whose ninth wave was almost empty).
+int strided_frames_per_unit(long long mids, long long batch, long long grid, int hoist)
+{
+    struct Key { long long mids, batch, grid; int hoist, fpu; };
+    static thread_local Key last{0, 0, 0, 0, 0};
+    if (last.mids == mids && last.batch == batch && last.grid == grid && last.hoist == hoist) return last.fpu;
+    long long best_cost = -1;
+    int best_fpu = 1;
+    std::vector<long long> load((size_t)grid);
+    // candidates: up to ~12 waves of units (more only adds hoists), at most 64 of them
+    long long max_chunks = (12 * grid + mids - 1) / mids;
+    if (max_chunks < 48) max_chunks = 48;
+    if (max_chunks > batch) max_chunks = batch;
+    const long long step = (max_chunks + 63) / 64;
+    for (long long want = 1; want <= max_chunks; want += (want < 16 ? 1 : step)) {
+        const long long fpu = (batch + want - 1) / want;
+        const long long chunks = (batch + fpu - 1) / fpu;
+        const long long units = mids * chunks;
+        std::fill(load.begin(), load.end(), 0);
+        for (long long u = 0; u < units; ++u) {
+            const long long c = u / mids;
+            const long long frames = (c + 1) * fpu <= batch ? fpu : batch - c * fpu;
+            load[(size_t)(u % grid)] += frames + hoist;
+        }
+        long long worst = 0;
+        for (long long v : load) worst = v > worst ? v : worst;
+        if (best_cost < 0 || worst < best_cost) { best_cost = worst; best_fpu = (int)fpu; }
+    }
+    last = Key{mids, batch, grid, hoist, best_fpu};
+    return best_fpu;
+}
+
 // top-bits pass of an NFFT >= 13 plan: kp.g in {4, 8}, kp.pb = NFFT - kp.g
-int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *twp, int num_sms, void *stream)
+int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *twp, int num_sms, void *stream,
+                          const TaylorDev *tay)
 {
     Strided16Params p{};
+    if (tay) p.tay = *tay;
     p.in = reinterpret_cast<const uint32_t *>(pd.kp.in);
     p.out = reinterpret_cast<uint32_t *>(pd.kp.out);
     p.twp = twp;
@@ -945,13 +991,8 @@ int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw
     const int G = pd.kp.g, C = 12 - G, mid_bits = p.n - G - C;
     const long long mids = 1ll << mid_bits;
     long long grid = 3ll * num_sms;
-    // enough work units to balance the grid, few enough to amortise the per-unit twiddle loads
-    long long chunks = (8 * grid + mids - 1) / mids;
-    if (chunks < 1) chunks = 1;
-    if (chunks > p.batch) chunks = p.batch;
-    p.frames_per_unit = (int)((p.batch + chunks - 1) / chunks);
-    chunks = (p.batch + p.frames_per_unit - 1) / p.frames_per_unit;
-    p.n_units = mids * chunks;
+    p.frames_per_unit = strided_frames_per_unit(mids, p.batch, grid, p.tay.on ? 2 : 1);
+    p.n_units = mids * ((p.batch + p.frames_per_unit - 1) / p.frames_per_unit);
     if (grid > p.n_units) grid = p.n_units;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool dw16 = p.dw == 16;

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include "intfft_arith.cuh"
+#include "intfft_taylor.cuh"
 
 namespace intfft {
 
@@ -34,10 +35,10 @@ struct Fast32Params {
     int dw, format;
     int in_sb, out_sb;       // scalar bytes of the containers read / written: 2 or 4
     int in_wrap;
-    int frames_per_unit;     // strided pass only
-    long long n_units;       // strided pass only
+    long long n_units;       // strided pass only: work items = column blocks per frame * batch
     CmultConsts cm;
     int lw_r[16], lw_i[16];  // lowest-round twiddles, index (1 << s) - 1 + k, s = 2, 3
+    TaylorDev tay;           // strided pass: .on = STAGE >= 11 twiddles recomputed on the device, tw ends at STAGE 11
 };
 
 // element (8-byte) index inside a 4096-sample tile -> slot in the padded exchange tile; additive for
@@ -589,14 +590,17 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_kernel(const __grid_con
     const int esz = 2 * p.in_sb;
     const int pb = p.n - G;
     const unsigned cmask = (1u << C) - 1u;
-    const int mid_bits = pb - C;
     const long long row_stride = 1ll << pb;
 
     int it = 0;
-    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const unsigned mid = (unsigned)(u & ((1ll << mid_bits) - 1));
-        const long long f0 = (u >> mid_bits) * p.frames_per_unit;
-        const long long f1 = (f0 + p.frames_per_unit < p.batch) ? f0 + p.frames_per_unit : p.batch;
+    // work items w = mid * batch + frame; CTA b owns the contiguous range [b T / G, (b + 1) T / G) (see intfft_fast16.cu)
+    long long w = p.n_units * blockIdx.x / gridDim.x;
+    const long long w_end = p.n_units * (blockIdx.x + 1) / gridDim.x;
+    while (w < w_end) {
+        const unsigned mid = (unsigned)(w / p.batch);
+        const long long f0 = w - (long long)mid * p.batch;
+        const long long f1 = (f0 + (w_end - w) < p.batch) ? f0 + (w_end - w) : p.batch;
+        w += f1 - f0;
         auto kidx = [&](unsigned l) { return ((l >> C) << pb) | (mid << C) | (l & cmask); };
 
         int uwr[15], uwi[15];
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < (1 << q); ++j) {
                 const int sgl = pb + (8 + q - C);
-                const int2 w = __ldg(p.tw + (1u << sgl) + (kidx(tid | ((unsigned)j << 8)) & ((1u << sgl) - 1u)));
+                const int2 w = hoist_twiddle(p.tw, p.tay, sgl, kidx(tid | ((unsigned)j << 8)) & ((1u << sgl) - 1u));
                 uwr[(1 << q) - 1 + j] = w.x;
                 uwi[(1 << q) - 1 + j] = w.y;
             }
@@ -616,7 +620,7 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_kernel(const __grid_con
                 const int q = w >= 7 ? 3 : (w >= 3 ? 2 : (w >= 1 ? 1 : 0));
                 const int j = w - ((1 << q) - 1);
                 const int sgl = pb + (4 + q - C);
-                midtw[w * 16 + lo4] = __ldg(p.tw + (1u << sgl) + (kidx((unsigned)lo4 | ((unsigned)j << 4)) & ((1u << sgl) - 1u)));
+                midtw[w * 16 + lo4] = hoist_twiddle(p.tw, p.tay, sgl, kidx((unsigned)lo4 | ((unsigned)j << 4)) & ((1u << sgl) - 1u));
             }
             __syncthreads();
         }

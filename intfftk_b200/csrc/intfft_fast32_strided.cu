@@ -23,7 +23,8 @@ bool fast32_supported(const intfft_generics &g)
 
 // twp / lwp_r / lwp_i: the same twiddles pre-shifted by 31 - sh_single (nullptr when the plan has none)
 int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
-                  int num_sms, void *stream, const int2 *twp, const int *lwp_r, const int *lwp_i, const unsigned *tw16)
+                  int num_sms, void *stream, const int2 *twp, const int *lwp_r, const int *lwp_i, const unsigned *tw16,
+                  const TaylorDev *tay)
 {
     f32::Fast32Params p{};
     p.in = pd.kp.in;
@@ -83,13 +84,12 @@ int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const 
     } else {
         const int G = pd.kp.g, C = 12 - G, mid_bits = p.n - G - C;
         const long long mids = 1ll << mid_bits;
-        long long chunks = (8 * grid + mids - 1) / mids;
-        if (chunks < 1) chunks = 1;
-        if (chunks > p.batch) chunks = p.batch;
-        p.frames_per_unit = (int)((p.batch + chunks - 1) / chunks);
-        chunks = (p.batch + p.frames_per_unit - 1) / p.frames_per_unit;
-        p.n_units = mids * chunks;
+        p.n_units = mids * p.batch;
         if (grid > p.n_units) grid = p.n_units;
+        if (tay) {
+            p.tay = *tay;
+            p.tay.e = kind == f32::KIND_SINGLE_PRE ? 31 - pd.kp.cm.sh_single : 0;    // what the table in p.tw carries
+        }
         e = f32_launch_strided(p, G, dit, mode, kind, (int)grid, stream);
     }
     count_launch();

@@ -19,6 +19,8 @@
 // Products are exact 64-bit: D = hi' * 2^32 + (signed) lo, D * W = mul.wide.s32(lo, W) + ((hi' * W) << 32).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "intfft_arith.cuh"
 
 namespace intfft {
@@ -35,6 +37,7 @@ struct Fast64Params {
     int dw, format;
     int in_sb, out_sb;       // scalar bytes of the containers read / written
     int in_wrap;
+    int prefetch;            // 1: input (32-bit containers) is staged through the per-warp landing area
     CmultConsts cm;
     int lw_r[16], lw_i[16];  // STAGE 2, 3 twiddles, index (1 << s) - 1 + k
 };
@@ -43,6 +46,20 @@ constexpr int kWarpSlots = 544;      // 512 samples + one 16-byte slot of skew p
 
 // sample index inside a warp's 512-sample chunk -> 16-byte slot; additive for disjoint bit sets
 __host__ __device__ constexpr unsigned phys64(unsigned i) { return i + (i >> 4); }
+
+// Input prefetch (32-bit containers, 8 bytes per sample: c3's second pass): the NEXT chunk's 4 KB land in a
+// warp-private area while the current chunk is computed — the warp fetches 512 contiguous bytes per cp.async
+// instruction, and nobody waits on HBM at the top of a chunk (without it this kernel spent more warp-cycles on
+// the long scoreboard than on anything else: two CTAs of 128-register threads cannot hide a DRAM round trip).
+// 8-byte element i sits at land[i + 2 * (i >> 4)]: one 16-byte slot of skew per 16 samples, so that both the
+// stride-16 (DIF, LDS.64) and the 16-contiguous (DIT, LDS.128) ownerships read it without bank conflicts.
+__host__ __device__ constexpr unsigned physL(unsigned i) { return i + 2u * (i >> 4); }
+constexpr int kLandElems = 576;      // physL(511) + 1 rounded up to whole 16-byte slots: 4608 bytes per warp
+__device__ __forceinline__ void cp_async_16z(void *smem_dst, const void *gsrc, unsigned bytes)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
 
 struct Stg64 {
     int s, ow, dtwc;
@@ -295,7 +312,7 @@ __device__ __forceinline__ void round64(int64_t (&re)[16], int64_t (&im)[16], co
     }
 }
 
-template <bool DIT, int MODE, int KIND>
+template <bool DIT, int MODE, int KIND, bool PF>
 __global__ void __launch_bounds__(256, 2) fast64_kernel(const __grid_constant__ Fast64Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -322,12 +339,54 @@ __global__ void __launch_bounds__(256, 2) fast64_kernel(const __grid_constant__ 
     const unsigned baseA = sub * 256u + l4, baseB = sub * 256u + 16u * l4;
     const unsigned pA = phys64(baseA), pB = phys64(baseB);
 
+    constexpr bool pf = PF;                            // in_sb == 4 (the launcher sized the landing area)
+    int2 *land = reinterpret_cast<int2 *>(smem_raw + 8 * kWarpSlots * 16) + warp * kLandElems;
+    // piece q = lane + 32 j holds samples 2q, 2q + 1: physL(2 lane + 64 j) = physL(2 lane) + 72 j
+    auto prefetch = [&](int64_t chunk) {
+        const int64_t g = chunk << 9;
+        const char *src = reinterpret_cast<const char *>(p.in) + g * 8 + 16u * lane;
+        int2 *dst = land + physL(2u * lane);
+        if (g + 512 <= p.total) {                      // whole chunk (all but possibly the last one): no predicates
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cp_async_16z(dst + 72 * j, src + 512 * j, 16u);
+        } else {                                       // total is a multiple of 256 samples: only the lower sub-block exists
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cp_async_16z(dst + 72 * j, src + 512 * j, 16u);
+#pragma unroll
+            for (int j = 4; j < 8; ++j) cp_async_16z(dst + 72 * j, p.in, 0u);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (pf && (int64_t)blockIdx.x * 8 + warp < p.n_chunks) prefetch((int64_t)blockIdx.x * 8 + warp);
+
     for (int64_t chunk = (int64_t)blockIdx.x * 8 + warp; chunk < p.n_chunks; chunk += (int64_t)gridDim.x * 8) {
         const int64_t g0 = chunk << 9;
         const bool active = g0 + sub * 256 < p.total;
         int64_t re[16], im[16];
-        // ---- first round: straight from HBM (container chosen outside the unrolled loop) ----
-        if (p.in_sb == 4) {
+        // ---- first round: from the landing area (prefetched one chunk ago) or straight from HBM ----
+        if (pf) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();                              // the other lanes' pieces have landed too
+            if (DIT) {
+                const int4 *own = reinterpret_cast<const int4 *>(land + physL(baseB));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int4 v = own[j];
+                    re[2 * j] = v.x; im[2 * j] = v.y;
+                    re[2 * j + 1] = v.z; im[2 * j + 1] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int2 v = land[physL(baseA) + 18u * m];          // physL(baseA + 16 m)
+                    re[m] = v.x;
+                    im[m] = v.y;
+                }
+            }
+            __syncwarp();                              // every lane has drained the area
+            const int64_t next = chunk + (int64_t)gridDim.x * 8;
+            if (next < p.n_chunks) prefetch(next);
+        } else if (p.in_sb == 4) {
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
                 int2 v = make_int2(0, 0);
@@ -412,8 +471,7 @@ struct Strided64Params {
     const int2 *tw;
     int64_t batch;
     int n, dw, format, in_sb, out_sb, in_wrap;
-    int frames_per_unit;
-    int64_t n_units;
+    int64_t n_units;         // work items = column blocks per frame * batch
     CmultConsts cm;
 };
 
@@ -428,14 +486,17 @@ __global__ void __launch_bounds__(256, 2) fast64_strided_kernel(const __grid_con
     const unsigned tid = threadIdx.x;
     const int pb = p.n - G;
     const unsigned cmask = (1u << C) - 1u;
-    const int mid_bits = pb - C;
     Fast64Params sp{};                              // what stage64<> reads
     sp.n = p.n; sp.dw = p.dw; sp.format = p.format; sp.cm = p.cm;
 
-    for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const unsigned mid = (unsigned)(u & ((1ll << mid_bits) - 1));
-        const int64_t f0 = (u >> mid_bits) * p.frames_per_unit;
-        const int64_t f1 = (f0 + p.frames_per_unit < p.batch) ? f0 + p.frames_per_unit : p.batch;
+    // work items w = mid * batch + frame; CTA b owns the contiguous range [b T / G, (b + 1) T / G) (see intfft_fast16.cu)
+    int64_t w = p.n_units * blockIdx.x / gridDim.x;
+    const int64_t w_end = p.n_units * (blockIdx.x + 1) / gridDim.x;
+    while (w < w_end) {
+        const unsigned mid = (unsigned)(w / p.batch);
+        const int64_t f0 = w - (int64_t)mid * p.batch;
+        const int64_t f1 = (f0 + (w_end - w) < p.batch) ? f0 + (w_end - w) : p.batch;
+        w += f1 - f0;
         auto kidx = [&](unsigned l) { return ((l >> C) << pb) | (mid << C) | (l & cmask); };
 
         int uwr[15], uwi[15];                       // round on local bits 8..11: STAGE pb + (8 + q - C)
@@ -544,8 +605,10 @@ template <bool DIT, int MODE> cudaError_t launch_k(const Fast64Params &p, int ki
     // KIND 0 (single DSP48 pair) needs dtwc < 28 and so never meets the "every width beyond 32 bits" rule of the
     // specialised instances; plans with such stages run the per-stage instance (3)
     if (kind < 1 || kind > 3) return cudaErrorInvalidValue;
-    K k = kind == 1 ? (K)fast64_kernel<DIT, MODE, 1> : (kind == 2 ? (K)fast64_kernel<DIT, MODE, 2> : (K)fast64_kernel<DIT, MODE, 3>);
-    const int smem = 8 * kWarpSlots * 16;
+    K k;
+    if (p.prefetch) k = kind == 1 ? (K)fast64_kernel<DIT, MODE, 1, true> : (kind == 2 ? (K)fast64_kernel<DIT, MODE, 2, true> : (K)fast64_kernel<DIT, MODE, 3, true>);
+    else k = kind == 1 ? (K)fast64_kernel<DIT, MODE, 1, false> : (kind == 2 ? (K)fast64_kernel<DIT, MODE, 2, false> : (K)fast64_kernel<DIT, MODE, 3, false>);
+    const int smem = 8 * kWarpSlots * 16 + (p.prefetch ? 8 * kLandElems * 8 : 0);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, smem, st>>>(p);
@@ -591,6 +654,7 @@ int launch_fast64(const PassDesc &pd, int mode, bool dit, const int2 *tw, const 
     p.in_sb = pd.kp.in_sb;
     p.out_sb = pd.kp.out_sb;
     p.in_wrap = pd.kp.in_wrap;
+    p.prefetch = (p.in_sb == 4 && getenv("INTFFT_F64_NO_PREFETCH") == nullptr) ? 1 : 0;
     p.cm = pd.kp.cm;
     for (int i = 0; i < 16; ++i) { p.lw_r[i] = lw_r[i]; p.lw_i[i] = lw_i[i]; }
     const int kind = fast64_uniform_kind(pd.kp, dit);
@@ -630,12 +694,7 @@ int launch_fast64_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw
     const int G = pd.kp.g, C = 12 - G, mid_bits = p.n - G - C;
     const int64_t mids = (int64_t)1 << mid_bits;
     int64_t grid = 2ll * num_sms;
-    int64_t chunks = (8 * grid + mids - 1) / mids;
-    if (chunks < 1) chunks = 1;
-    if (chunks > p.batch) chunks = p.batch;
-    p.frames_per_unit = (int)((p.batch + chunks - 1) / chunks);
-    chunks = (p.batch + p.frames_per_unit - 1) / p.frames_per_unit;
-    p.n_units = mids * chunks;
+    p.n_units = mids * p.batch;
     if (grid > p.n_units) grid = p.n_units;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cudaError_t e;

@@ -29,6 +29,17 @@ CmultConsts cmult_consts(int twdl_width, int xser);
 // fills re/im[0 .. 2^stage) with the stream rom_twiddle_int(STAGE = stage) produces.
 void twiddle_stage_table(int stage, int twdl_width, int xser, int32_t *re, int32_t *im);
 
+// ---- on-device Taylor twiddles (intfft_taylor.cuh): what a kernel needs to recompute W_s[k], s >= 11 ----
+struct TaylorDev {
+    const int2 *rom9;      // rom_twiddle_int's coarse ROM of depth 9 (512 entries, device memory)
+    int on;                // 0: every twiddle comes from the tables
+    int tw, xs;            // TWDL_WIDTH, XSHIFT (21 NEW / 23 OLD)
+    int e;                 // left shift applied to the result (pre-shifted-table kernels), else 0
+    int mathpi[9];         // MATHPI of STAGE 11 .. 19
+};
+// fills the 512-entry coarse ROM (as (c_i, s_i) pairs) and the nine MATHPI constants
+void taylor_consts(int twdl_width, int xser, int32_t *rom_c, int32_t *rom_s, int *mathpi, int *xshift);
+
 // ---- kernel-facing description of one pass over the data --------------------------------------
 enum LaneKind { LANE_I32_P64 = 0, LANE_I64_P64 = 1, LANE_I64_P128 = 2 };
 enum ModeKind { MODE_TRUNC = 0, MODE_ROUND = 1, MODE_UNSCALED = 2 };
@@ -93,6 +104,9 @@ struct Plan {
     int lw32_r[16] = {0}, lw32_i[16] = {0};  // same, not pre-shifted (32-bit-lane kernels)
     int2 *d_twp32 = nullptr;     // twiddles << (31 - sh_single) for the 32-bit-lane TRUNCATE kernels (KIND_SINGLE_PRE)
     int lwp32_r[16] = {0}, lwp32_i[16] = {0};
+    int2 *d_rom9 = nullptr;      // coarse ROM of the on-device Taylor path
+    TaylorDev tay{};             // .on = 1: STAGE >= 12 tables are not even built (NFFT >= 17 plans on the strided kernels)
+    TaylorDev tay16{};           // the same with the packed-16 kernels' pre-shift
     unsigned *d_tw12p = nullptr; // STAGE-12 twiddles packed {re:16 | im:16} (one-pass 8192-point kernel, TWDL_WIDTH <= 16)
     void *scratch[2] = {nullptr, nullptr};
     size_t scratch_bytes[2] = {0, 0};
@@ -117,11 +131,13 @@ int launch_fast16_n13(const PassDesc &pd, int mode, bool dit, const int2 *twp, c
                       int num_sms, void *stream);
 int launch_fast16_pair(const PassDesc &pd, int mode, const int2 *twp, const int *lw_r, const int *lw_i, int num_sms,
                        void *stream);
-int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *twp, int num_sms, void *stream);
+int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *twp, int num_sms, void *stream,
+                          const TaylorDev *tay = nullptr);
 bool fast32_supported(const intfft_generics &g);
 int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const int *lw_r, const int *lw_i,
                   int num_sms, void *stream, const int2 *twp = nullptr, const int *lwp_r = nullptr,
-                  const int *lwp_i = nullptr, const unsigned *tw16 = nullptr);
+                  const int *lwp_i = nullptr, const unsigned *tw16 = nullptr, const TaylorDev *tay = nullptr);
+int launch_taylor_table(const TaylorDev &tay, int stage, int2 *d_out, void *stream);     // test hook (intfft_util.cu)
 // 64-bit-lane kernel for the lowest eight stage bits (intfft_fast64.cu)
 int fast64_uniform_kind(const PassParams &kp, bool dit);
 int launch_fast64_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw, int num_sms, void *stream);

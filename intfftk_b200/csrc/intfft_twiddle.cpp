@@ -80,6 +80,16 @@ void twiddle_stage_table(int stage, int awd, int xser, int32_t *re, int32_t *im)
     }
 }
 
+void taylor_consts(int awd, int xser, int32_t *rom_c, int32_t *rom_s, int *mathpi, int *xshift)
+{
+    std::vector<int64_t> qc, qs;
+    quarter_wave(9, awd, qc, qs);
+    for (int i = 0; i < 512; ++i) { rom_c[i] = (int32_t)qc[i]; rom_s[i] = (int32_t)qs[i]; }
+    for (int stage = 11; stage <= 19; ++stage)
+        mathpi[stage - 11] = (int)std::llround(M_PI * std::ldexp(1.0, 13 - (stage - 11) - (xser ? 2 : 0)));
+    *xshift = xser ? 21 : 23;
+}
+
 CmultConsts cmult_consts(int tw, int xser)
 {
     CmultConsts c{};

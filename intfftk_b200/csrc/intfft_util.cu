@@ -10,6 +10,7 @@
 #include <atomic>
 
 #include "intfft_internal.h"
+#include "intfft_taylor.cuh"
 
 namespace intfft {
 
@@ -208,6 +209,23 @@ int launch_bitrev(int n, int sb, long long batch, const void *in, void *out, voi
     if (sb == 2) bitrev_kernel<short2><<<(int)grid, side * side, smem, st>>>((const short2 *)in, (short2 *)out, n, h, n_tiles);
     else if (sb == 4) bitrev_kernel<int2><<<(int)grid, side * side, smem, st>>>((const int2 *)in, (int2 *)out, n, h, n_tiles);
     else bitrev_kernel<longlong2><<<(int)grid, side * side, smem, st>>>((const longlong2 *)in, (longlong2 *)out, n, h, n_tiles);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// test hook: the device Taylor function over a whole stage (intfft_twiddles_device)
+namespace {
+__global__ void taylor_table_kernel(const __grid_constant__ TaylorDev t, int stage, int2 *out)
+{
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < (1u << stage)) out[k] = taylor_twiddle(t, stage, k);
+}
+}  // namespace
+
+int launch_taylor_table(const TaylorDev &tay, int stage, int2 *d_out, void *stream)
+{
+    const unsigned n = 1u << stage;
+    taylor_table_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tay, stage, d_out);
     count_launch();
     return (int)cudaGetLastError();
 }

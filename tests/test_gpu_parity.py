@@ -587,3 +587,50 @@ def test_python_mirror_rejects_wrong_tensors(ib):
     with pytest.raises(ib.IntfftError):
         pair.exec(x, torch.empty((4, 256, 2), dtype=torch.int32, device="cuda"))
     pair.close(); core.close()
+
+
+# ---- on-device Taylor twiddles (intfft_taylor.cuh): STAGE >= 11 recomputed where the strided kernels hoist them ----
+@pytest.mark.parametrize("tw,xser", [(16, "NEW"), (16, "OLD"), (8, "NEW"), (12, "OLD"), (17, "NEW"), (18, "NEW"),
+                                      (19, "NEW"), (24, "OLD"), (25, "OLD"), (27, "NEW")])
+def test_device_taylor_function_equals_table(ib, tw, xser):
+    """The kernels' device function over whole stages == the host generator == row_twiddle_tay
+    (rom_twiddle_int.vhd:215-246, row_twiddle_tay.vhd:123-382), STAGE 11..19, both XSER, narrow and wide twiddles."""
+    g = ib.Generics(TWDL_WIDTH=tw, XSER=xser)
+    for stage in (11, 12, 13, 15, 16, 18, 19):
+        dre, dim = ib.twiddles_device(g, stage)
+        hre, him = ib.twiddles(g, stage)
+        assert np.array_equal(dre, hre) and np.array_equal(dim, him), (tw, xser, stage)
+
+
+@pytest.mark.parametrize("kw,batch", [
+    (dict(NFFT=17, DATA_WIDTH=16, FORMAT=0), 3),                    # packed-16 strided-8 + 9 bits (default threshold)
+    (dict(NFFT=19, DATA_WIDTH=12, FORMAT=0, RNDMODE=1), 2),
+    (dict(NFFT=18, DATA_WIDTH=18, FORMAT=0), 2),                    # 32-bit lanes, pre-shifted twiddles in the DIT pass
+    (dict(NFFT=17, DATA_WIDTH=14, FORMAT=1), 2),                    # UNSCALED growth to 31 bits, mixed arrangements
+    (dict(NFFT=17, DATA_WIDTH=18, TWDL_WIDTH=24, FORMAT=0, XSER="OLD"), 2),
+])
+def test_device_taylor_plans_match_oracle(ib, oracle, kw, batch):
+    """NFFT >= 17 plans on the strided kernels run WITHOUT STAGE >= 12 tables: bit-exact vs the oracle, both directions."""
+    for direction in (0, 1):
+        if ib.validate(ib.Generics(**kw), direction) != 0:
+            continue
+        got, want = _run_both(ib, oracle, batch, seed=170 + direction, via="device", direction=direction, **kw)
+        assert np.array_equal(got, want), (kw, direction)
+
+
+@pytest.mark.parametrize("kw", [dict(NFFT=14, DATA_WIDTH=16, FORMAT=0), dict(NFFT=16, DATA_WIDTH=16, FORMAT=0),
+                                dict(NFFT=15, DATA_WIDTH=18, FORMAT=0), dict(NFFT=16, DATA_WIDTH=16, FORMAT=1)])
+def test_device_taylor_equals_table_path(ib, kw, monkeypatch):
+    """Same plan with the threshold lowered (device Taylor from NFFT 13 on) and raised (tables only): identical output."""
+    g = ib.Generics(**kw)
+    n = 1 << g.NFFT
+    for direction in (0, 1):
+        x = ib.fill_random(torch.empty(4 * n * 2, dtype=torch.int16 if g.DATA_WIDTH <= 16 else torch.int32, device="cuda"),
+                           g.DATA_WIDTH, 99 + direction).reshape(4, n, 2)
+        monkeypatch.setenv("INTFFT_TAYLOR_MIN_NFFT", "13")
+        a = ib.Core(g, 4, direction)
+        monkeypatch.setenv("INTFFT_TAYLOR_MIN_NFFT", "99")
+        b = ib.Core(g, 4, direction)
+        monkeypatch.delenv("INTFFT_TAYLOR_MIN_NFFT")
+        assert torch.equal(a.exec(x), b.exec(x)), (kw, direction)
+        a.close(); b.close()
