@@ -30,6 +30,31 @@ __device__ __forceinline__ void fly_split(int &ar, int &ai, int &br, int &bi, in
     ai = xi;
 }
 
+// Three-multiply complex product (Gauss) on pre-shifted twiddle triples a = wr << 15, b = -(wr + wi) << 15,
+// c = (wi - wr) << 15 (|wr +- wi| <= sqrt(2) * 32767 < 2^16, so the triples fit an int32):
+//   k1 = a (dr + di);  re = k1 + di b = (dr wr - di wi) << 15;  im = k1 + dr c = (dr wi + di wr) << 15   (exact, mod 2^64)
+// The kept slice wrap17(S >> 16) sits at bits 31..47 of the 64-bit word: one funnel shift + SGXT per output.
+// 3 IMAD.WIDE + 1 IADD + 2 SHF instead of 4 IMAD.WIDE / IMAD.HI.
+__device__ __forceinline__ int slice31(long long t)
+{
+    unsigned lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(t));
+    return sgxt32((int)__funnelshift_l(lo, hi, 1), 17);
+}
+__device__ __forceinline__ void fly_k3(int &ar, int &ai, int &br, int &bi, int a, int b, int c)
+{
+    const int dr = bi, di = br;                              // swapped re / im into the multiplier
+    const long long k1 = (long long)a * (dr + di);
+    const long long tr = k1 + (long long)di * b;
+    const long long ti = k1 + (long long)dr * c;
+    const int hi = slice31(tr), hr = slice31(ti);            // (BW >> 1), outputs swapped back
+    const int xr = sra1(ar) + hr, xi = sra1(ai) + hi;
+    br = msub2(hr, xr);
+    bi = msub2(hi, xi);
+    ar = xr;
+    ai = xi;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256, 3) fly_loop(const int2 *in, int2 *out, const int2 *tw, int iters, const __grid_constant__ Fast32Params p)
 {
@@ -43,6 +68,23 @@ __global__ void __launch_bounds__(256, 3) fly_loop(const int2 *in, int2 *out, co
     for (int i = 0; i < 15; ++i) { const int2 w = tw[tid * 15 + i]; uwr[i] = w.x; uwi[i] = w.y; }
     for (int it = 0; it < iters; ++it) {
         if (KIND == 0) round32<4, true, MODE_TRUNC, KIND_SINGLE>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
+        if (KIND == 2) round32<4, true, MODE_TRUNC, KIND_SINGLE_PRE>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
+        if (KIND == 3) {          // production butterfly, twiddles from a shared table (round B of the 8192-point kernel)
+            const int2 *t = reinterpret_cast<const int2 *>(smem) + (tid & 15u);
+            round32<4, true, MODE_TRUNC, KIND_SINGLE_PRE>(re, im, p, 4, TwSmem32{t, 16}, false, false);
+        }
+        if (KIND == 4) {          // three-multiply butterfly, twiddle triples from a shared table
+            const int4 *t = reinterpret_cast<const int4 *>(smem) + (tid & 15u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    if (m & (1 << q)) continue;
+                    const int w = (1 << q) - 1 + (m & ((1 << q) - 1));
+                    const int4 tw3 = t[w * 16];
+                    fly_k3(re[m].f, im[m].f, re[m | (1 << q)].f, im[m | (1 << q)].f, tw3.x, tw3.y, tw3.z);
+                }
+        }
         if (KIND == 1) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -56,7 +98,7 @@ __global__ void __launch_bounds__(256, 3) fly_loop(const int2 *in, int2 *out, co
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) out[(blockIdx.x * 256 + tid) * 16 + i] = make_int2(re[i].f, im[i].f);
-    if (iters < 0) smem[tid] = 0;
+    if (iters < 0) smem[tid] = 0;          // (the tables are never initialised: timing only)
 }
 
 template <int KIND> void run(const char *name, int smem)
@@ -86,5 +128,8 @@ int main()
     run<0>("fly32 DIT TRUNC (IMAD.WIDE), 6 CTAs/SM", 0);
     run<1>("split-operand 32-bit IMAD form, 3 CTAs/SM", 72 * 1024);
     run<1>("split-operand 32-bit IMAD form, 6 CTAs/SM", 0);
+    run<2>("production KIND_SINGLE_PRE, register twiddles, 3 CTAs/SM", 72 * 1024);
+    run<3>("production KIND_SINGLE_PRE, shared-table twiddles, 3 CTAs/SM", 72 * 1024);
+    run<4>("three-multiply (Gauss) form, shared-table triples, 3 CTAs/SM", 72 * 1024);
     return 0;
 }
