@@ -22,9 +22,11 @@
 //   * rounds exchange through a double-buffered padded tile whose skew is additive, so every
 //     shared-memory address is "per-round base register + compile-time immediate" and every access
 //     pattern (32-bit at stride 256 / 16, 128-bit contiguous) is bank-conflict free for N = 4096.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include <vector>
 
@@ -901,6 +903,183 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Strided pass, G = 8 (NFFT 16..20: 256 rows x 16 columns), column block moved by the TMA engine in BOTH
+// directions: one thread issues cp.async.bulk.tensor.2d for the frame's 256 x 64-byte block (the "stride-2^s
+// shuffle" of the delay lines, int_delay_line.vhd:52-104, done by the copy engine instead of 4 cp.async + address
+// arithmetic per thread), the last round's results go to a dense tile and leave as ONE tensor store instead of
+// 16 four-byte STG per thread.  The whole batch is one 2-D tensor: 2^(NFFT-8) columns x (batch * 256) rows.
+// Dense landing tiles (TMA cannot skew): word l = 16 row + column.  Round "bits 8..11" touches l = tid + 256 m
+// (conflict-free), round "bits 4..7" l = (tid & 15) + 256 (tid >> 4) + 16 m (two-way conflicts between the
+// half-warps on the ONE access set of four that meets a dense tile; the exchange tile keeps the phys() skew).
+constexpr unsigned kStridedTmaSmem = kSmemHead + kTileWords * 4 + 3 * 16384;
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <bool DIT, bool DW16, int MODE>
+__global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid_constant__ Strided16Params p,
+                                                                    const __grid_constant__ CUtensorMap map_in,
+                                                                    const __grid_constant__ CUtensorMap map_out)
+{
+    constexpr int G = 8, C = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);
+    uint32_t *work = reinterpret_cast<uint32_t *>(smem_raw + kSmemHead);
+    uint32_t(*land)[4096] = reinterpret_cast<uint32_t(*)[4096]>(smem_raw + kSmemHead + kTileWords * 4);
+    uint32_t *otile = land[2];
+
+    const unsigned tid = threadIdx.x;
+    const int sh_full = p.sh_full, sh_half = p.sh_half;
+    const int pb = p.n - G;
+    const unsigned cmask = (1u << C) - 1u;
+    const int mid_bits = pb - C;
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_in)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
+    }
+    __syncthreads();
+
+    unsigned it = 0, phase = 0;                      // phase bit b = parity the next wait on bar[b] expects
+    auto load = [&](unsigned buf, unsigned mid, long long f) {          // thread 0 only
+        mbar_expect_tx(&bar[buf], 16384u);
+        tma_load_2d(land[buf], &map_in, (int)(mid << C), (int)(f << G), &bar[buf]);
+    };
+    // ownerships inside the 256 x 16 block: round on local bits 8..11 / on local bits 4..7
+    const unsigned base8 = tid, base4 = (tid & 15u) | ((tid >> 4) << 8);
+    const unsigned pbase8 = phys(base8), pbase4 = phys(base4);
+
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const unsigned mid = (unsigned)(u & ((1ll << mid_bits) - 1));
+        const long long f0 = (u >> mid_bits) * p.frames_per_unit;
+        const long long f1 = (f0 + p.frames_per_unit < p.batch) ? f0 + p.frames_per_unit : p.batch;
+        auto kidx = [&](unsigned l) { return ((l >> C) << pb) | (mid << C) | (l & cmask); };
+        if (tid == 0 && f0 < f1) load(it & 1u, mid, f0);
+
+        int uwr[15], uwi[15];                       // round on local bits 8..11
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < (1 << q); ++j) {
+                const int sgl = pb + (8 + q - C);
+                const int2 w = hoist_twiddle(p.twp, p.tay, sgl, kidx(tid | ((unsigned)j << 8)) & ((1u << sgl) - 1u));
+                uwr[(1 << q) - 1 + j] = w.x;
+                uwi[(1 << q) - 1 + j] = w.y;
+            }
+        __syncthreads();                            // previous unit's readers of the table are done
+        if (tid < 240) {                            // round on local bits 4..7: table[w][tid & 15]
+            const int w = tid >> 4, lo4 = tid & 15;
+            const int q = w >= 7 ? 3 : (w >= 3 ? 2 : (w >= 1 ? 1 : 0));
+            const int j = w - ((1 << q) - 1);
+            const int sgl = pb + (4 + q - C);
+            midtw[w * 16 + lo4] = hoist_twiddle(p.twp, p.tay, sgl, kidx((unsigned)lo4 | ((unsigned)j << 4)) & ((1u << sgl) - 1u));
+        }
+        __syncthreads();
+
+        for (long long f = f0; f < f1; ++f, ++it) {
+            const unsigned buf = it & 1u;
+            // the other landing tile was drained in the previous frame's first round, which every thread left
+            // before that frame's last barrier: refill it while this frame is computed
+            if (tid == 0 && f + 1 < f1) load(buf ^ 1u, mid, f + 1);
+            mbar_wait(&bar[buf], (phase >> buf) & 1u);
+            phase ^= 1u << buf;
+            const uint32_t *st = land[buf];
+            int re[16], im[16];
+            constexpr bool RAW = !DIT && DW16;
+            if (!DIT) {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) unpack<DW16>(st[base8 + 256u * m], p.dw, re[m], im[m]);
+                round_regs<8, 4, false, DW16, MODE, RAW>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+                    work[pbase8 + phys((unsigned)m << 8)] = (RAW && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632) : pack(re[m], im[m]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) unpack<DW16>(st[base4 + 16u * m], p.dw, re[m], im[m]);
+                round_regs<4, 4, true, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, false, sh_full, sh_half);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) work[pbase4 + phys((unsigned)m << 4)] = pack(re[m], im[m]);
+            }
+            // the previous frame's tensor store has finished READING the output tile before anyone rewrites it
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+            if (!DIT) {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) unpack<true>(work[pbase4 + phys((unsigned)m << 4)], p.dw, re[m], im[m]);
+                round_regs<4, 4, false, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, false, sh_full, sh_half);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) otile[base4 + 16u * m] = pack(re[m], im[m]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) unpack<true>(work[pbase8 + phys((unsigned)m << 8)], p.dw, re[m], im[m]);
+                round_regs<8, 4, true, DW16, MODE, false>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) otile[base8 + 256u * m] = pack(re[m], im[m]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the TMA engine
+            __syncthreads();                        // also: every thread has left the exchange tile
+            if (tid == 0) tma_store_2d(&map_out, (int)(mid << C), (int)(f << G), otile);
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+// the whole batch as a 2-D tensor of packed samples: 2^pb columns x (batch * 2^G) rows; box = 2^C x 2^G
+bool make_block_map(CUtensorMap *map, const void *base, int pb, long long batch)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)1 << pb, (cuuint64_t)batch << 8};
+    const cuuint64_t strides[1] = {((cuuint64_t)4) << pb};
+    const cuuint32_t box[2] = {16, 256}, estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool DIT, bool DW16>
+cudaError_t launch_strided_tma_k(const Strided16Params &p, int mode, int grid, cudaStream_t st)
+{
+    CUtensorMap mi, mo;
+    if (!make_block_map(&mi, p.in, p.n - 8, p.batch) || !make_block_map(&mo, p.out, p.n - 8, p.batch)) return cudaErrorNotSupported;
+    auto k = mode == MODE_ROUND ? fast16_strided_tma_kernel<DIT, DW16, MODE_ROUND> : fast16_strided_tma_kernel<DIT, DW16, MODE_TRUNC>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedTmaSmem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, 256, kStridedTmaSmem, st>>>(p, mi, mo);
+    return cudaGetLastError();
+}
+
 template <int G, bool DIT, bool DW16>
 cudaError_t launch_strided_k(const Strided16Params &p, int mode, int grid, cudaStream_t st)
 {
@@ -997,7 +1176,13 @@ int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool dw16 = p.dw == 16;
     cudaError_t e;
-    if (G == 4) {
+    // G = 8: the TMA-staged variant (INTFFT_STRIDED_TMA=0 keeps the cp.async / STG one)
+    const char *tma_env = std::getenv("INTFFT_STRIDED_TMA");
+    const bool tma_now = G == 8 && !(tma_env && tma_env[0] == '0');
+    if (tma_now) {
+        if (!dit) e = dw16 ? launch_strided_tma_k<false, true>(p, mode, (int)grid, st) : launch_strided_tma_k<false, false>(p, mode, (int)grid, st);
+        else e = dw16 ? launch_strided_tma_k<true, true>(p, mode, (int)grid, st) : launch_strided_tma_k<true, false>(p, mode, (int)grid, st);
+    } else if (G == 4) {
         if (!dit) e = dw16 ? launch_strided_k<4, false, true>(p, mode, (int)grid, st) : launch_strided_k<4, false, false>(p, mode, (int)grid, st);
         else e = dw16 ? launch_strided_k<4, true, true>(p, mode, (int)grid, st) : launch_strided_k<4, true, false>(p, mode, (int)grid, st);
     } else if (G == 8) {
