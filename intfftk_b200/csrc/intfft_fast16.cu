@@ -927,12 +927,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-template <bool DIT, bool DW16, int MODE>
+template <int G, bool DIT, bool DW16, int MODE>
 __global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid_constant__ Strided16Params p,
                                                                     const __grid_constant__ CUtensorMap map_in,
                                                                     const __grid_constant__ CUtensorMap map_out)
 {
-    constexpr int G = 8, C = 4;
+    constexpr int C = 12 - G;                       // G = 8: 256 rows x 16 columns; G = 4: 16 rows x 256 columns
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);
@@ -981,15 +981,15 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid
                 uwr[(1 << q) - 1 + j] = w.x;
                 uwi[(1 << q) - 1 + j] = w.y;
             }
-        __syncthreads();                            // previous unit's readers of the table are done
-        if (tid < 240) {                            // round on local bits 4..7: table[w][tid & 15]
+        if (G == 8) __syncthreads();                // previous unit's readers of the table are done
+        if (G == 8 && tid < 240) {                  // round on local bits 4..7: table[w][tid & 15]
             const int w = tid >> 4, lo4 = tid & 15;
             const int q = w >= 7 ? 3 : (w >= 3 ? 2 : (w >= 1 ? 1 : 0));
             const int j = w - ((1 << q) - 1);
             const int sgl = pb + (4 + q - C);
             midtw[w * 16 + lo4] = hoist_twiddle(p.twp, p.tay, sgl, kidx((unsigned)lo4 | ((unsigned)j << 4)) & ((1u << sgl) - 1u));
         }
-        __syncthreads();
+        if (G == 8) __syncthreads();
 
         for (long long f = f0; f < f1; ++f, ++it) {
             const unsigned buf = it & 1u;
@@ -1001,35 +1001,45 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid
             const uint32_t *st = land[buf];
             int re[16], im[16];
             constexpr bool RAW = !DIT && DW16;
-            if (!DIT) {
+            if (G == 4) {                           // single round on local bits 8..11: landing tile -> output tile
 #pragma unroll
                 for (int m = 0; m < 16; ++m) unpack<DW16>(st[base8 + 256u * m], p.dw, re[m], im[m]);
-                round_regs<8, 4, false, DW16, MODE, RAW>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
-#pragma unroll
-                for (int m = 0; m < 16; ++m)
-                    work[pbase8 + phys((unsigned)m << 8)] = (RAW && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632) : pack(re[m], im[m]);
-            } else {
-#pragma unroll
-                for (int m = 0; m < 16; ++m) unpack<DW16>(st[base4 + 16u * m], p.dw, re[m], im[m]);
-                round_regs<4, 4, true, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, false, sh_full, sh_half);
-#pragma unroll
-                for (int m = 0; m < 16; ++m) work[pbase4 + phys((unsigned)m << 4)] = pack(re[m], im[m]);
-            }
-            // the previous frame's tensor store has finished READING the output tile before anyone rewrites it
-            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncthreads();
-            if (!DIT) {
-#pragma unroll
-                for (int m = 0; m < 16; ++m) unpack<true>(work[pbase4 + phys((unsigned)m << 4)], p.dw, re[m], im[m]);
-                round_regs<4, 4, false, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, false, sh_full, sh_half);
-#pragma unroll
-                for (int m = 0; m < 16; ++m) otile[base4 + 16u * m] = pack(re[m], im[m]);
-            } else {
-#pragma unroll
-                for (int m = 0; m < 16; ++m) unpack<true>(work[pbase8 + phys((unsigned)m << 8)], p.dw, re[m], im[m]);
-                round_regs<8, 4, true, DW16, MODE, false>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
+                round_regs<8, 4, DIT, DW16, MODE, false>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();                    // the previous frame's tensor store has finished reading the output tile
 #pragma unroll
                 for (int m = 0; m < 16; ++m) otile[base8 + 256u * m] = pack(re[m], im[m]);
+            } else {
+                if (!DIT) {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) unpack<DW16>(st[base8 + 256u * m], p.dw, re[m], im[m]);
+                    round_regs<8, 4, false, DW16, MODE, RAW>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
+#pragma unroll
+                    for (int m = 0; m < 16; ++m)
+                        work[pbase8 + phys((unsigned)m << 8)] = (RAW && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632) : pack(re[m], im[m]);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) unpack<DW16>(st[base4 + 16u * m], p.dw, re[m], im[m]);
+                    round_regs<4, 4, true, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, false, sh_full, sh_half);
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) work[pbase4 + phys((unsigned)m << 4)] = pack(re[m], im[m]);
+                }
+                // the previous frame's tensor store has finished READING the output tile before anyone rewrites it
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+                if (!DIT) {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) unpack<true>(work[pbase4 + phys((unsigned)m << 4)], p.dw, re[m], im[m]);
+                    round_regs<4, 4, false, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, false, sh_full, sh_half);
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) otile[base4 + 16u * m] = pack(re[m], im[m]);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) unpack<true>(work[pbase8 + phys((unsigned)m << 8)], p.dw, re[m], im[m]);
+                    round_regs<8, 4, true, DW16, MODE, false>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) otile[base8 + 256u * m] = pack(re[m], im[m]);
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the TMA engine
             __syncthreads();                        // also: every thread has left the exchange tile
@@ -1056,24 +1066,24 @@ EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 // the whole batch as a 2-D tensor of packed samples: 2^pb columns x (batch * 2^G) rows; box = 2^C x 2^G
-bool make_block_map(CUtensorMap *map, const void *base, int pb, long long batch)
+bool make_block_map(CUtensorMap *map, const void *base, int pb, int g, long long batch)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)1 << pb, (cuuint64_t)batch << 8};
+    const cuuint64_t dims[2] = {(cuuint64_t)1 << pb, (cuuint64_t)batch << g};
     const cuuint64_t strides[1] = {((cuuint64_t)4) << pb};
-    const cuuint32_t box[2] = {16, 256}, estr[2] = {1, 1};
+    const cuuint32_t box[2] = {1u << (12 - g), 1u << g}, estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <bool DIT, bool DW16>
+template <int G, bool DIT, bool DW16>
 cudaError_t launch_strided_tma_k(const Strided16Params &p, int mode, int grid, cudaStream_t st)
 {
     CUtensorMap mi, mo;
-    if (!make_block_map(&mi, p.in, p.n - 8, p.batch) || !make_block_map(&mo, p.out, p.n - 8, p.batch)) return cudaErrorNotSupported;
-    auto k = mode == MODE_ROUND ? fast16_strided_tma_kernel<DIT, DW16, MODE_ROUND> : fast16_strided_tma_kernel<DIT, DW16, MODE_TRUNC>;
+    if (!make_block_map(&mi, p.in, p.n - G, G, p.batch) || !make_block_map(&mo, p.out, p.n - G, G, p.batch)) return cudaErrorNotSupported;
+    auto k = mode == MODE_ROUND ? fast16_strided_tma_kernel<G, DIT, DW16, MODE_ROUND> : fast16_strided_tma_kernel<G, DIT, DW16, MODE_TRUNC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedTmaSmem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, kStridedTmaSmem, st>>>(p, mi, mo);
@@ -1178,10 +1188,13 @@ int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw
     cudaError_t e;
     // G = 8: the TMA-staged variant (INTFFT_STRIDED_TMA=0 keeps the cp.async / STG one)
     const char *tma_env = std::getenv("INTFFT_STRIDED_TMA");
-    const bool tma_now = G == 8 && !(tma_env && tma_env[0] == '0');
-    if (tma_now) {
-        if (!dit) e = dw16 ? launch_strided_tma_k<false, true>(p, mode, (int)grid, st) : launch_strided_tma_k<false, false>(p, mode, (int)grid, st);
-        else e = dw16 ? launch_strided_tma_k<true, true>(p, mode, (int)grid, st) : launch_strided_tma_k<true, false>(p, mode, (int)grid, st);
+    const bool tma_now = !(tma_env && tma_env[0] == '0');
+    if (tma_now && G == 8) {
+        if (!dit) e = dw16 ? launch_strided_tma_k<8, false, true>(p, mode, (int)grid, st) : launch_strided_tma_k<8, false, false>(p, mode, (int)grid, st);
+        else e = dw16 ? launch_strided_tma_k<8, true, true>(p, mode, (int)grid, st) : launch_strided_tma_k<8, true, false>(p, mode, (int)grid, st);
+    } else if (tma_now && G == 4) {
+        if (!dit) e = dw16 ? launch_strided_tma_k<4, false, true>(p, mode, (int)grid, st) : launch_strided_tma_k<4, false, false>(p, mode, (int)grid, st);
+        else e = dw16 ? launch_strided_tma_k<4, true, true>(p, mode, (int)grid, st) : launch_strided_tma_k<4, true, false>(p, mode, (int)grid, st);
     } else if (G == 4) {
         if (!dit) e = dw16 ? launch_strided_k<4, false, true>(p, mode, (int)grid, st) : launch_strided_k<4, false, false>(p, mode, (int)grid, st);
         else e = dw16 ? launch_strided_k<4, true, true>(p, mode, (int)grid, st) : launch_strided_k<4, true, false>(p, mode, (int)grid, st);
