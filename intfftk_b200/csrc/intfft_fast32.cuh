@@ -18,6 +18,7 @@
 
 #include "intfft_arith.cuh"
 #include "intfft_taylor.cuh"
+#include "intfft_tma.cuh"
 
 namespace intfft {
 
@@ -690,6 +691,174 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_kernel(const __grid_con
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Strided pass, G = 8, column block moved by 2-D TMA in both directions (see intfft_tma.cuh; packed-16 twin:
+// fast16_strided_tma_kernel).  Shared memory: [head | ONE exchange tile | two dense landing tiles]; a frame's
+// landing tile, drained by the first round, takes the last round's results and is the source of the frame's
+// tensor store, so a third tile is not needed and two CTAs still fit on an SM (102 KB each).
+// A sample is 1 or 2 words (in_sb / out_sb = 2 or 4); dense tile: sample l = 16 row + column at l * (words per sample).
+constexpr unsigned kLand32 = 4096 * 8;
+constexpr unsigned kStridedTmaSmem32 = kHead32 + kTile8 * 8 + 2 * kLand32;
+
+template <bool DIT, int MODE, int KIND>
+__global__ void __launch_bounds__(256, 2) fast32_strided_tma_kernel(const __grid_constant__ Fast32Params p,
+                                                                    const __grid_constant__ CUtensorMap map_in,
+                                                                    const __grid_constant__ CUtensorMap map_out)
+{
+    constexpr int G = 8, C = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);
+    int2 *work = reinterpret_cast<int2 *>(smem_raw + kHead32);
+    unsigned char *land0 = smem_raw + kHead32 + kTile8 * 8;
+
+    const unsigned tid = threadIdx.x;
+    const int pb = p.n - G;
+    const unsigned cmask = (1u << C) - 1u;
+    const int iw = p.in_sb >> 1, ow = p.out_sb >> 1;          // words per sample in / out
+
+    if (tid == 0) {
+        tma::mbar_init(&bar[0], 1);
+        tma::mbar_init(&bar[1], 1);
+        tma::mbar_fence_init();
+        tma::prefetch_map(&map_in);
+        tma::prefetch_map(&map_out);
+    }
+    __syncthreads();
+
+    unsigned it = 0, phase = 0;
+    auto load = [&](unsigned buf, unsigned mid, long long f) {          // thread 0 only
+        tma::mbar_expect_tx(&bar[buf], 4096u * 4u * iw);
+        tma::load_2d(land0 + buf * kLand32, &map_in, (int)((mid << C) * iw), (int)(f << G), &bar[buf]);
+    };
+    const unsigned base8 = tid, base4 = (tid & 15u) | ((tid >> 4) << 8);
+    const unsigned pbase8 = phys8(base8), pbase4 = phys8(base4);
+    constexpr unsigned baseF_is8 = DIT ? 0u : 1u;                        // first round: bits 8..11 (DIF) or 4..7 (DIT)
+    const unsigned baseF = baseF_is8 ? base8 : base4, stepF = baseF_is8 ? 256u : 16u;
+    const unsigned baseL = baseF_is8 ? base4 : base8, stepL = baseF_is8 ? 16u : 256u;
+
+    // work items w = mid * batch + frame; CTA b owns the contiguous range [b T / G, (b + 1) T / G) (see intfft_fast16.cu)
+    long long w = p.n_units * blockIdx.x / gridDim.x;
+    const long long w_end = p.n_units * (blockIdx.x + 1) / gridDim.x;
+    while (w < w_end) {
+        const unsigned mid = (unsigned)(w / p.batch);
+        const long long f0 = w - (long long)mid * p.batch;
+        const long long f1 = (f0 + (w_end - w) < p.batch) ? f0 + (w_end - w) : p.batch;
+        w += f1 - f0;
+        auto kidx = [&](unsigned l) { return ((l >> C) << pb) | (mid << C) | (l & cmask); };
+        if (tid == 0) {
+            tma::store_wait_read<1>();               // the store two frames back read from the tile about to be refilled
+            load(it & 1u, mid, f0);
+        }
+
+        int uwr[15], uwi[15];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < (1 << q); ++j) {
+                const int sgl = pb + (8 + q - C);
+                const int2 tw = hoist_twiddle(p.tw, p.tay, sgl, kidx(tid | ((unsigned)j << 8)) & ((1u << sgl) - 1u));
+                uwr[(1 << q) - 1 + j] = tw.x;
+                uwi[(1 << q) - 1 + j] = tw.y;
+            }
+        __syncthreads();
+        if (tid < 240) {
+            const int ww = tid >> 4, lo4 = tid & 15;
+            const int q = ww >= 7 ? 3 : (ww >= 3 ? 2 : (ww >= 1 ? 1 : 0));
+            const int j = ww - ((1 << q) - 1);
+            const int sgl = pb + (4 + q - C);
+            midtw[ww * 16 + lo4] = hoist_twiddle(p.tw, p.tay, sgl, kidx((unsigned)lo4 | ((unsigned)j << 4)) & ((1u << sgl) - 1u));
+        }
+        __syncthreads();
+
+        for (long long f = f0; f < f1; ++f, ++it) {
+            const unsigned buf = it & 1u;
+            if (tid == 0 && f + 1 < f1) {
+                tma::store_wait_read<0>();           // the previous frame's store has read the other tile: refill it
+                load(buf ^ 1u, mid, f + 1);
+            }
+            tma::mbar_wait(&bar[buf], (phase >> buf) & 1u);
+            phase ^= 1u << buf;
+            unsigned char *tile = land0 + buf * kLand32;
+            V re[16], im[16];
+            // ---- first round, from the dense landing tile ----
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                int a, b;
+                const unsigned l = baseF + stepF * m;
+                if (p.in_sb == 2) {
+                    const unsigned x = reinterpret_cast<const unsigned *>(tile)[l];
+                    a = (int)(short)(x & 0xffffu);
+                    b = (int)x >> 16;
+                } else {
+                    const int2 v = reinterpret_cast<const int2 *>(tile)[l];
+                    a = v.x;
+                    b = v.y;
+                }
+                if (p.in_wrap) { a = sx(a, p.dw); b = sx(b, p.dw); }
+                re[m] = mk(a);
+                im[m] = mk(b);
+            }
+            if (!DIT) round32<4, DIT, MODE, KIND, TwRegs32, true>(re, im, p, pb + 8 - C, TwRegs32{uwr, uwi}, false, false);
+            else round32<4, DIT, MODE, KIND, TwSmem32, true>(re, im, p, pb + 4 - C, TwSmem32{midtw + (tid & 15u), 16}, false, false);
+            {
+                const unsigned pbase = baseF_is8 ? pbase8 : pbase4;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) work[pbase + phys8(stepF * m)] = make_int2(re[m].f, im[m].f);
+            }
+            __syncthreads();                         // exchange tile complete; every thread has drained the landing tile
+            {
+                const unsigned pbase = baseF_is8 ? pbase4 : pbase8;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) { const int2 v = work[pbase + phys8(stepL * m)]; re[m] = mk(v.x); im[m] = mk(v.y); }
+            }
+            if (!DIT) round32<4, DIT, MODE, KIND, TwSmem32, true>(re, im, p, pb + 4 - C, TwSmem32{midtw + (tid & 15u), 16}, false, false);
+            else round32<4, DIT, MODE, KIND, TwRegs32, true>(re, im, p, pb + 8 - C, TwRegs32{uwr, uwi}, false, false);
+            // ---- results into the (drained) landing tile, dense, in the output container ----
+            if (p.out_sb == 2) {
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+                    reinterpret_cast<unsigned *>(tile)[baseL + stepL * m] = __byte_perm((unsigned)re[m].f, (unsigned)im[m].f, 0x5410);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) reinterpret_cast<int2 *>(tile)[baseL + stepL * m] = make_int2(re[m].f, im[m].f);
+            }
+            tma::fence_async();
+            __syncthreads();                         // also: every thread has left the exchange tile
+            if (tid == 0) tma::store_2d(&map_out, (int)((mid << C) * ow), (int)(f << G), tile);
+        }
+    }
+    if (tid == 0) tma::store_wait_all();
+}
+
+template <typename K> cudaError_t launch_any_tma(K k, const Fast32Params &p, int grid, cudaStream_t st)
+{
+    CUtensorMap mi, mo;
+    const uint64_t rows = (uint64_t)p.batch << 8;
+    const uint32_t iw = p.in_sb >> 1, ow = p.out_sb >> 1;
+    if (!tma::make_map_u32(&mi, p.in, ((uint64_t)iw) << (p.n - 8), rows, 16 * iw, 256) ||
+        !tma::make_map_u32(&mo, p.out, ((uint64_t)ow) << (p.n - 8), rows, 16 * ow, 256))
+        return cudaErrorNotSupported;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedTmaSmem32);
+    if (e != cudaSuccess) return e;
+    k<<<grid, 256, kStridedTmaSmem32, st>>>(p, mi, mo);
+    return cudaGetLastError();
+}
+template <bool DIT> cudaError_t launch_strided_tma(const Fast32Params &p, int mode, int kind, int grid, cudaStream_t st)
+{
+    if constexpr (DIT) {
+        if (kind == KIND_SINGLE_PRE) return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_TRUNC, KIND_SINGLE_PRE>, p, grid, st);
+    }
+    switch (mode * 2 + kind) {
+    case MODE_TRUNC * 2 + 0: return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_TRUNC, KIND_SINGLE>, p, grid, st);
+    case MODE_TRUNC * 2 + 1: return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_TRUNC, KIND_MIXED>, p, grid, st);
+    case MODE_ROUND * 2 + 0: return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_ROUND, KIND_SINGLE>, p, grid, st);
+    case MODE_ROUND * 2 + 1: return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_ROUND, KIND_MIXED>, p, grid, st);
+    case MODE_UNSCALED * 2 + 0: return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_UNSCALED, KIND_SINGLE>, p, grid, st);
+    default: return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_UNSCALED, KIND_MIXED>, p, grid, st);
+    }
+}
 
 template <typename K> cudaError_t launch_any(K k, const Fast32Params &p, int grid, cudaStream_t st)
 {

@@ -9,7 +9,12 @@ int f32_launch_strided(const f32::Fast32Params &p, int g, bool dit, int mode, in
 {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (g == 4) return (int)(dit ? f32::launch_strided<4, true>(p, mode, kind, grid, st) : f32::launch_strided<4, false>(p, mode, kind, grid, st));
-    if (g == 8) return (int)(dit ? f32::launch_strided<8, true>(p, mode, kind, grid, st) : f32::launch_strided<8, false>(p, mode, kind, grid, st));
+    if (g == 8) {
+        const char *tma_env = std::getenv("INTFFT_STRIDED_TMA");          // =0: the cp.async / STG form
+        if (!(tma_env && tma_env[0] == '0'))
+            return (int)(dit ? f32::launch_strided_tma<true>(p, mode, kind, grid, st) : f32::launch_strided_tma<false>(p, mode, kind, grid, st));
+        return (int)(dit ? f32::launch_strided<8, true>(p, mode, kind, grid, st) : f32::launch_strided<8, false>(p, mode, kind, grid, st));
+    }
     return (int)cudaErrorInvalidValue;
 }
 
