@@ -701,12 +701,12 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_kernel(const __grid_con
 constexpr unsigned kLand32 = 4096 * 8;
 constexpr unsigned kStridedTmaSmem32 = kHead32 + kTile8 * 8 + 2 * kLand32;
 
-template <bool DIT, int MODE, int KIND>
+template <int G, bool DIT, int MODE, int KIND>
 __global__ void __launch_bounds__(256, 2) fast32_strided_tma_kernel(const __grid_constant__ Fast32Params p,
                                                                     const __grid_constant__ CUtensorMap map_in,
                                                                     const __grid_constant__ CUtensorMap map_out)
 {
-    constexpr int G = 8, C = 4;
+    constexpr int C = 12 - G;                       // G = 8: 256 rows x 16 columns; G = 4: 16 rows x 256 columns
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);
@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_tma_kernel(const __grid
     const unsigned tid = threadIdx.x;
     const int pb = p.n - G;
     const unsigned cmask = (1u << C) - 1u;
-    const int iw = p.in_sb >> 1, ow = p.out_sb >> 1;          // words per sample in / out
+    const int iw = p.in_sb >> 1;                              // words per sample in the input container
 
     if (tid == 0) {
         tma::mbar_init(&bar[0], 1);
@@ -730,13 +730,13 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_tma_kernel(const __grid
     unsigned it = 0, phase = 0;
     auto load = [&](unsigned buf, unsigned mid, long long f) {          // thread 0 only
         tma::mbar_expect_tx(&bar[buf], 4096u * 4u * iw);
-        tma::load_2d(land0 + buf * kLand32, &map_in, (int)((mid << C) * iw), (int)(f << G), &bar[buf]);
+        tma::load_2d(land0 + buf * kLand32, &map_in, (int)(mid << C), (int)(f << G), &bar[buf]);
     };
     const unsigned base8 = tid, base4 = (tid & 15u) | ((tid >> 4) << 8);
     const unsigned pbase8 = phys8(base8), pbase4 = phys8(base4);
-    constexpr unsigned baseF_is8 = DIT ? 0u : 1u;                        // first round: bits 8..11 (DIF) or 4..7 (DIT)
+    constexpr unsigned baseF_is8 = (G == 4 || !DIT) ? 1u : 0u;           // first round: bits 8..11 (DIF, G = 4) or 4..7 (DIT)
     const unsigned baseF = baseF_is8 ? base8 : base4, stepF = baseF_is8 ? 256u : 16u;
-    const unsigned baseL = baseF_is8 ? base4 : base8, stepL = baseF_is8 ? 16u : 256u;
+    const unsigned baseL = G == 4 ? base8 : (baseF_is8 ? base4 : base8), stepL = G == 4 ? 256u : (baseF_is8 ? 16u : 256u);
 
     // work items w = mid * batch + frame; CTA b owns the contiguous range [b T / G, (b + 1) T / G) (see intfft_fast16.cu)
     long long w = p.n_units * blockIdx.x / gridDim.x;
@@ -762,15 +762,15 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_tma_kernel(const __grid
                 uwr[(1 << q) - 1 + j] = tw.x;
                 uwi[(1 << q) - 1 + j] = tw.y;
             }
-        __syncthreads();
-        if (tid < 240) {
+        if (G == 8) __syncthreads();
+        if (G == 8 && tid < 240) {
             const int ww = tid >> 4, lo4 = tid & 15;
             const int q = ww >= 7 ? 3 : (ww >= 3 ? 2 : (ww >= 1 ? 1 : 0));
             const int j = ww - ((1 << q) - 1);
             const int sgl = pb + (4 + q - C);
             midtw[ww * 16 + lo4] = hoist_twiddle(p.tw, p.tay, sgl, kidx((unsigned)lo4 | ((unsigned)j << 4)) & ((1u << sgl) - 1u));
         }
-        __syncthreads();
+        if (G == 8) __syncthreads();
 
         for (long long f = f0; f < f1; ++f, ++it) {
             const unsigned buf = it & 1u;
@@ -800,21 +800,26 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_tma_kernel(const __grid
                 re[m] = mk(a);
                 im[m] = mk(b);
             }
-            if (!DIT) round32<4, DIT, MODE, KIND, TwRegs32, true>(re, im, p, pb + 8 - C, TwRegs32{uwr, uwi}, false, false);
-            else round32<4, DIT, MODE, KIND, TwSmem32, true>(re, im, p, pb + 4 - C, TwSmem32{midtw + (tid & 15u), 16}, false, false);
-            {
-                const unsigned pbase = baseF_is8 ? pbase8 : pbase4;
+            if (G == 4) {                            // the pass's only round; results go straight back into the tile
+                round32<4, DIT, MODE, KIND, TwRegs32, true>(re, im, p, pb + 8 - C, TwRegs32{uwr, uwi}, false, false);
+                __syncthreads();                     // every thread has drained the landing tile
+            } else {
+                if (!DIT) round32<4, DIT, MODE, KIND, TwRegs32, true>(re, im, p, pb + 8 - C, TwRegs32{uwr, uwi}, false, false);
+                else round32<4, DIT, MODE, KIND, TwSmem32, true>(re, im, p, pb + 4 - C, TwSmem32{midtw + (tid & 15u), 16}, false, false);
+                {
+                    const unsigned pbase = baseF_is8 ? pbase8 : pbase4;
 #pragma unroll
-                for (int m = 0; m < 16; ++m) work[pbase + phys8(stepF * m)] = make_int2(re[m].f, im[m].f);
-            }
-            __syncthreads();                         // exchange tile complete; every thread has drained the landing tile
-            {
-                const unsigned pbase = baseF_is8 ? pbase4 : pbase8;
+                    for (int m = 0; m < 16; ++m) work[pbase + phys8(stepF * m)] = make_int2(re[m].f, im[m].f);
+                }
+                __syncthreads();                         // exchange tile complete; every thread has drained the landing tile
+                {
+                    const unsigned pbase = baseF_is8 ? pbase4 : pbase8;
 #pragma unroll
-                for (int m = 0; m < 16; ++m) { const int2 v = work[pbase + phys8(stepL * m)]; re[m] = mk(v.x); im[m] = mk(v.y); }
+                    for (int m = 0; m < 16; ++m) { const int2 v = work[pbase + phys8(stepL * m)]; re[m] = mk(v.x); im[m] = mk(v.y); }
+                }
+                if (!DIT) round32<4, DIT, MODE, KIND, TwSmem32, true>(re, im, p, pb + 4 - C, TwSmem32{midtw + (tid & 15u), 16}, false, false);
+                else round32<4, DIT, MODE, KIND, TwRegs32, true>(re, im, p, pb + 8 - C, TwRegs32{uwr, uwi}, false, false);
             }
-            if (!DIT) round32<4, DIT, MODE, KIND, TwSmem32, true>(re, im, p, pb + 4 - C, TwSmem32{midtw + (tid & 15u), 16}, false, false);
-            else round32<4, DIT, MODE, KIND, TwRegs32, true>(re, im, p, pb + 8 - C, TwRegs32{uwr, uwi}, false, false);
             // ---- results into the (drained) landing tile, dense, in the output container ----
             if (p.out_sb == 2) {
 #pragma unroll
@@ -826,37 +831,37 @@ __global__ void __launch_bounds__(256, 2) fast32_strided_tma_kernel(const __grid
             }
             tma::fence_async();
             __syncthreads();                         // also: every thread has left the exchange tile
-            if (tid == 0) tma::store_2d(&map_out, (int)((mid << C) * ow), (int)(f << G), tile);
+            if (tid == 0) tma::store_2d(&map_out, (int)(mid << C), (int)(f << G), tile);
         }
     }
     if (tid == 0) tma::store_wait_all();
 }
 
-template <typename K> cudaError_t launch_any_tma(K k, const Fast32Params &p, int grid, cudaStream_t st)
+template <int G, typename K> cudaError_t launch_any_tma(K k, const Fast32Params &p, int grid, cudaStream_t st)
 {
     CUtensorMap mi, mo;
-    const uint64_t rows = (uint64_t)p.batch << 8;
-    const uint32_t iw = p.in_sb >> 1, ow = p.out_sb >> 1;
-    if (!tma::make_map_u32(&mi, p.in, ((uint64_t)iw) << (p.n - 8), rows, 16 * iw, 256) ||
-        !tma::make_map_u32(&mo, p.out, ((uint64_t)ow) << (p.n - 8), rows, 16 * ow, 256))
+    const uint64_t rows = (uint64_t)p.batch << G;
+    const uint32_t cols = 1u << (12 - G);
+    if (!tma::make_map(&mi, p.in, p.in_sb >> 1, (uint64_t)1 << (p.n - G), rows, cols, 1u << G) ||
+        !tma::make_map(&mo, p.out, p.out_sb >> 1, (uint64_t)1 << (p.n - G), rows, cols, 1u << G))
         return cudaErrorNotSupported;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedTmaSmem32);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, kStridedTmaSmem32, st>>>(p, mi, mo);
     return cudaGetLastError();
 }
-template <bool DIT> cudaError_t launch_strided_tma(const Fast32Params &p, int mode, int kind, int grid, cudaStream_t st)
+template <int G, bool DIT> cudaError_t launch_strided_tma(const Fast32Params &p, int mode, int kind, int grid, cudaStream_t st)
 {
     if constexpr (DIT) {
-        if (kind == KIND_SINGLE_PRE) return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_TRUNC, KIND_SINGLE_PRE>, p, grid, st);
+        if (kind == KIND_SINGLE_PRE) return launch_any_tma<G>(fast32_strided_tma_kernel<G, DIT, MODE_TRUNC, KIND_SINGLE_PRE>, p, grid, st);
     }
     switch (mode * 2 + kind) {
-    case MODE_TRUNC * 2 + 0: return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_TRUNC, KIND_SINGLE>, p, grid, st);
-    case MODE_TRUNC * 2 + 1: return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_TRUNC, KIND_MIXED>, p, grid, st);
-    case MODE_ROUND * 2 + 0: return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_ROUND, KIND_SINGLE>, p, grid, st);
-    case MODE_ROUND * 2 + 1: return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_ROUND, KIND_MIXED>, p, grid, st);
-    case MODE_UNSCALED * 2 + 0: return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_UNSCALED, KIND_SINGLE>, p, grid, st);
-    default: return launch_any_tma(fast32_strided_tma_kernel<DIT, MODE_UNSCALED, KIND_MIXED>, p, grid, st);
+    case MODE_TRUNC * 2 + 0: return launch_any_tma<G>(fast32_strided_tma_kernel<G, DIT, MODE_TRUNC, KIND_SINGLE>, p, grid, st);
+    case MODE_TRUNC * 2 + 1: return launch_any_tma<G>(fast32_strided_tma_kernel<G, DIT, MODE_TRUNC, KIND_MIXED>, p, grid, st);
+    case MODE_ROUND * 2 + 0: return launch_any_tma<G>(fast32_strided_tma_kernel<G, DIT, MODE_ROUND, KIND_SINGLE>, p, grid, st);
+    case MODE_ROUND * 2 + 1: return launch_any_tma<G>(fast32_strided_tma_kernel<G, DIT, MODE_ROUND, KIND_MIXED>, p, grid, st);
+    case MODE_UNSCALED * 2 + 0: return launch_any_tma<G>(fast32_strided_tma_kernel<G, DIT, MODE_UNSCALED, KIND_SINGLE>, p, grid, st);
+    default: return launch_any_tma<G>(fast32_strided_tma_kernel<G, DIT, MODE_UNSCALED, KIND_MIXED>, p, grid, st);
     }
 }
 

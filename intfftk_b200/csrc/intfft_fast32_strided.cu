@@ -8,11 +8,14 @@ namespace intfft {
 int f32_launch_strided(const f32::Fast32Params &p, int g, bool dit, int mode, int kind, int grid, void *stream)
 {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (g == 4) return (int)(dit ? f32::launch_strided<4, true>(p, mode, kind, grid, st) : f32::launch_strided<4, false>(p, mode, kind, grid, st));
+    const char *tma_env = std::getenv("INTFFT_STRIDED_TMA");              // =0: the cp.async / STG form
+    const bool use_tma = !(tma_env && tma_env[0] == '0');
+    if (g == 4) {
+        if (use_tma) return (int)(dit ? f32::launch_strided_tma<4, true>(p, mode, kind, grid, st) : f32::launch_strided_tma<4, false>(p, mode, kind, grid, st));
+        return (int)(dit ? f32::launch_strided<4, true>(p, mode, kind, grid, st) : f32::launch_strided<4, false>(p, mode, kind, grid, st));
+    }
     if (g == 8) {
-        const char *tma_env = std::getenv("INTFFT_STRIDED_TMA");          // =0: the cp.async / STG form
-        if (!(tma_env && tma_env[0] == '0'))
-            return (int)(dit ? f32::launch_strided_tma<true>(p, mode, kind, grid, st) : f32::launch_strided_tma<false>(p, mode, kind, grid, st));
+        if (use_tma) return (int)(dit ? f32::launch_strided_tma<8, true>(p, mode, kind, grid, st) : f32::launch_strided_tma<8, false>(p, mode, kind, grid, st));
         return (int)(dit ? f32::launch_strided<8, true>(p, mode, kind, grid, st) : f32::launch_strided<8, false>(p, mode, kind, grid, st));
     }
     return (int)cudaErrorInvalidValue;

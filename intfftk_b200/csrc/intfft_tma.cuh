@@ -66,18 +66,20 @@ inline EncodeTiledFn encode_tiled_fn()
     }();
     return fn;
 }
-// A batch of frames as a 2-D tensor of 32-bit words: `row_words` words per row, `rows` rows, box = box_words x box_rows
-// (a sample is 1 word in packed-16 containers, 2 words in 32-bit ones).  No swizzle: the landing tile is dense.
-inline bool make_map_u32(CUtensorMap *map, const void *base, uint64_t row_words, uint64_t rows, uint32_t box_words, uint32_t box_rows)
+// A batch of frames as a 2-D tensor of samples: `row_samples` samples per row, `rows` rows, box = box_samples x box_rows.
+// A sample is one 32-bit word (packed-16 containers) or one 64-bit word (32-bit containers); coordinates are in samples.
+// No swizzle: the landing tile is dense.
+inline bool make_map(CUtensorMap *map, const void *base, int sample_words, uint64_t row_samples, uint64_t rows,
+                     uint32_t box_samples, uint32_t box_rows)
 {
     EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn) return false;
-    const cuuint64_t dims[2] = {row_words, rows};
-    const cuuint64_t strides[1] = {row_words * 4};
-    const cuuint32_t box[2] = {box_words, box_rows}, estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (!fn || box_samples > 256 || box_rows > 256) return false;
+    const cuuint64_t dims[2] = {row_samples, rows};
+    const cuuint64_t strides[1] = {row_samples * 4 * (uint64_t)sample_words};
+    const cuuint32_t box[2] = {box_samples, box_rows}, estr[2] = {1, 1};
+    return fn(map, sample_words == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2,
+              const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace tma

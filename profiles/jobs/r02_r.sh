@@ -14,5 +14,7 @@ for env in ("0", "1"):
         q.time_plan(512, steps=20, direction=d, NFFT=18, DATA_WIDTH=18, FORMAT=0)
         q.time_plan(1024, steps=20, direction=d, NFFT=17, DATA_WIDTH=14, FORMAT=1)
         q.time_plan(2048, steps=20, direction=d, NFFT=16, DATA_WIDTH=16, FORMAT=1)
+        q.time_plan(8192, steps=20, direction=d, NFFT=14, DATA_WIDTH=18, FORMAT=0)
+        q.time_plan(2048, steps=20, direction=d, NFFT=16, DATA_WIDTH=18, FORMAT=0)
 PY
 cat gpurun_out/r02r_times.txt
