@@ -634,3 +634,34 @@ def test_device_taylor_equals_table_path(ib, kw, monkeypatch):
         monkeypatch.delenv("INTFFT_TAYLOR_MIN_NFFT")
         assert torch.equal(a.exec(x), b.exec(x)), (kw, direction)
         a.close(); b.close()
+
+
+# ---- strided passes: 2-D TMA (default) and the cp.async / STG form (INTFFT_STRIDED_TMA=0) must agree ----
+@pytest.mark.parametrize("kw", [
+    dict(NFFT=20, DATA_WIDTH=16, FORMAT=0),                    # c4 geometry: packed-16, 256 rows x 16 columns
+    dict(NFFT=17, DATA_WIDTH=12, FORMAT=0, RNDMODE=1),         # DATA_WIDTH < 16 unpack, ROUNDING
+    dict(NFFT=15, DATA_WIDTH=16, FORMAT=0),                    # packed-16, 16 rows x 256 columns
+    dict(NFFT=16, DATA_WIDTH=24, FORMAT=1),                    # c3: 32-bit lanes, 8-byte samples, mixed arrangements
+    dict(NFFT=18, DATA_WIDTH=18, FORMAT=0),                    # 32-bit lanes, pre-shifted twiddles in the DIT pass
+    dict(NFFT=14, DATA_WIDTH=18, FORMAT=0),                    # 32-bit lanes, 16 rows x 256 columns (UINT64 tensor map)
+    dict(NFFT=16, DATA_WIDTH=16, FORMAT=1),                    # packed input container, 32-bit output container
+])
+def test_strided_tma_equals_cp_async_form(ib, oracle, kw, monkeypatch):
+    g = ib.Generics(**kw)
+    n = 1 << g.NFFT
+    og_args = (g.NFFT, g.DATA_WIDTH, g.TWDL_WIDTH, g.FORMAT, g.RNDMODE, 1 if g.XSER == "NEW" else 0, g.USE_FLY)
+    for direction in (0, 1):
+        if ib.validate(g, direction) != 0:
+            continue
+        x = oracle.fill_random(3 * n * 2, g.DATA_WIDTH, 31 + direction).reshape(3, n, 2)
+        d_in = torch.from_numpy(x).cuda()
+        core = ib.Core(g, 3, direction)
+        monkeypatch.setenv("INTFFT_STRIDED_TMA", "0")
+        a = core.exec(d_in).clone()
+        monkeypatch.setenv("INTFFT_STRIDED_TMA", "1")
+        b = core.exec(d_in).clone()
+        monkeypatch.delenv("INTFFT_STRIDED_TMA")
+        core.close()
+        assert torch.equal(a, b), (kw, direction)
+        want = oracle.batch(oracle.generics(*og_args, direction), x, 0)
+        assert np.array_equal(b.cpu().numpy(), want), (kw, direction)
