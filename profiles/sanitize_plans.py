@@ -12,6 +12,8 @@ PLANS = [  # (NFFT, DW, FORMAT, RND, direction, batch)
     (13, 18, 0, 0, 1, 5), (13, 18, 1, 0, 1, 4), (13, 18, 0, 0, 0, 4), (13, 16, 1, 0, 1, 3),
     (12, 18, 0, 0, 0, 5), (12, 18, 0, 0, 1, 5), (10, 20, 0, 1, 1, 9), (11, 18, 1, 0, 0, 6), (12, 16, 1, 0, 1, 5),
     (14, 18, 0, 0, 0, 2), (16, 24, 1, 0, 0, 2), (8, 40, 0, 0, 1, 9), (7, 16, 1, 0, 0, 6),
+    # round 2: TMA-staged strided passes (both geometries, both lane families, several frames per CTA), on-device Taylor
+    (17, 16, 0, 0, 0, 3), (17, 16, 0, 0, 1, 3), (15, 16, 0, 0, 0, 5), (18, 18, 0, 0, 1, 2), (14, 18, 0, 0, 1, 5), (16, 24, 1, 0, 1, 2),
 ]
 for nfft, dw, fmt, rnd, direction, batch in PLANS:
     g = ib.Generics(NFFT=nfft, DATA_WIDTH=dw, FORMAT=fmt, RNDMODE=rnd)
