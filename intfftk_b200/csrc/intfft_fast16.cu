@@ -231,15 +231,16 @@ struct TwRegs {
     const int (&i)[15];
     __device__ __forceinline__ void operator()(int w, int &wr, int &wi) const { wr = r[w]; wi = i[w]; }
 };
-struct TwSmem {          // table[w][tid & 15] of pre-shifted (re, im); one LDS.64 per butterfly
+template <int PITCH> struct TwSmemP {   // table[w][low bits of tid] of pre-shifted (re, im); one LDS.64 per butterfly
     const int2 *t;
     __device__ __forceinline__ void operator()(int w, int &wr, int &wi) const
     {
-        const int2 v = t[w * 16];
+        const int2 v = t[w * PITCH];
         wr = v.x;
         wi = v.y;
     }
 };
+using TwSmem = TwSmemP<16>;
 
 // MIDSM: keep the middle round's 15 twiddles in a 1920-byte shared table instead of 30 registers, which
 // brings the kernel under 85 registers so that three CTAs (24 warps) fit on one SM.
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
     // warp instruction would touch 32 separate 16-byte pieces at a 64-byte pitch, so the WARP fetches its
     // 2 KB as 512 contiguous bytes per cp.async instruction into a skewed landing tile, one tile ahead.
     constexpr bool CP_IN = DIT;
-    static_assert(!MIDSM || (NR == 3 && R0 == 4), "MIDSM is for the three-round 4+4+4 schedule");
+    static_assert(!MIDSM || NR == 3, "MIDSM is for the three-round schedules (R0 + 4 + 4 stages)");
     // dynamic shared memory: [bar 2 x u64 | pad to 128] [mid twiddles 15 x 16 x int2] [work 2 x kTileWords]
     //                        [stage 2 x 4096 (DIF only)]
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -322,12 +323,12 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
     if (CP_IN && (long long)blockIdx.x < p.n_tiles) prefetch_warp(blockIdx.x);
 
     // ---- per-thread constant twiddles of the upper rounds ----
-    if (MIDSM) {                                   // table[w][lo4], w = (1 << q) - 1 + j, stage = R0 + q
-        if (tid < 240) {
-            const int w = tid >> 4, lo4 = tid & 15;
+    if (MIDSM) {                                   // table[w][low R0 bits of tid], w = (1 << q) - 1 + j, stage = R0 + q
+        if (tid < (15u << R0)) {
+            const int w = tid >> R0, lo4 = tid & ((1u << R0) - 1u);
             const int q = w >= 7 ? 3 : (w >= 3 ? 2 : (w >= 1 ? 1 : 0));
             const int j = w - ((1 << q) - 1);
-            midtw[w * 16 + lo4] = __ldg(p.twp + (1u << (R0 + q)) + lo4 + ((unsigned)j << R0));
+            midtw[(w << R0) + lo4] = __ldg(p.twp + (1u << (R0 + q)) + lo4 + ((unsigned)j << R0));
         }
         __syncthreads();
     }
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
             // then hold raw products and are packed from their upper half-words
             constexpr bool RAW = !CD && DW16 && R0 >= 2;
             if (r == 0) round_regs<0, R0, CD, DW16, MODE, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
-            else if (r == 1 && MIDSM) round_regs<R0, 4, CD, DW16, MODE, RAW>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
+            else if (r == 1 && MIDSM) round_regs<R0, 4, CD, DW16, MODE, RAW>(re, im, TwSmemP<(1 << R0)>{midtw + (tid & ((1u << R0) - 1u))}, tid_odd, sh_full, sh_half);
             else if (r == 1) round_regs<R0, 4, CD, DW16, MODE, RAW>(re, im, TwRegs{uwr[0], uwi[0]}, tid_odd, sh_full, sh_half);
             else round_regs<R0 + 4, 4, CD, DW16, MODE, RAW>(re, im, TwRegs{uwr[NU - 1], uwi[NU - 1]}, tid_odd, sh_full, sh_half);
 
@@ -1105,7 +1106,7 @@ template <int NLOG2, bool DIT, bool DW16, bool NAT = false, bool PAIR = false>
 cudaError_t launch_k(const Fast16Params &p, int mode, int grid, cudaStream_t st)
 {
     const int smem = kSmemHead + 2 * kTileWords * 4 + (DIT ? (int)kTileWords * 4 : 2 * 4096 * 4);
-    constexpr bool MIDSM = (NLOG2 == 12);
+    constexpr bool MIDSM = (NLOG2 >= 9 && NLOG2 <= 12);      // every three-round schedule: 80 registers, three CTAs per SM
     auto k = mode == MODE_ROUND ? fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_ROUND, NAT, PAIR> : fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_TRUNC, NAT, PAIR>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -1221,7 +1222,7 @@ int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const
     p.sh_full = 32 - p.dw;
     p.sh_half = 33 - p.dw;
     for (int i = 0; i < 16; ++i) { p.lw_r[i] = lw_r[i]; p.lw_i[i] = lw_i[i]; }
-    long long grid = (pd.kp.g == 12 ? 3ll : 2ll) * num_sms;
+    long long grid = ((pd.kp.g >= 9 && pd.kp.g <= 12) ? 3ll : 2ll) * num_sms;   // three-round schedules: three CTAs per SM
     if (grid > p.n_tiles) grid = p.n_tiles;
     if (grid < 1) grid = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1298,7 +1299,7 @@ int launch_fast16_pair(const PassDesc &pd, int mode, const int2 *twp, const int 
     p.sh_full = 32 - p.dw;
     p.sh_half = 33 - p.dw;
     for (int i = 0; i < 16; ++i) { p.lw_r[i] = lw_r[i]; p.lw_i[i] = lw_i[i]; }
-    long long grid = (pd.kp.g == 12 ? 3ll : 2ll) * num_sms;
+    long long grid = ((pd.kp.g >= 9 && pd.kp.g <= 12) ? 3ll : 2ll) * num_sms;   // three-round schedules: three CTAs per SM
     if (grid > p.n_tiles) grid = p.n_tiles;
     if (grid < 1) grid = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
