@@ -519,10 +519,18 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
             } else if (COALESCE) {
                 // the warp's own runs of the tile, 512 contiguous bytes per store (up to the run length)
                 __syncwarp();
+                if (full) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const unsigned i = warp_piece(c);
-                    if (full || g0 + i < p.total) *reinterpret_cast<uint4 *>(p.out + g0 + i) = *reinterpret_cast<const uint4 *>(sm + phys(i));
+                    for (int c = 0; c < 4; ++c) {
+                        const unsigned i = warp_piece(c);
+                        *reinterpret_cast<uint4 *>(p.out + g0 + i) = *reinterpret_cast<const uint4 *>(sm + phys(i));
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const unsigned i = warp_piece(c);
+                        if (g0 + i < p.total) *reinterpret_cast<uint4 *>(p.out + g0 + i) = *reinterpret_cast<const uint4 *>(sm + phys(i));
+                    }
                 }
             } else if (NAT) {
                 __syncthreads();

@@ -438,10 +438,14 @@ __global__ void __launch_bounds__(256, 2) fast64_kernel(const __grid_constant__ 
 #pragma unroll
             for (int m = 0; m < 16; ++m) sm[pB + m] = make_longlong2(re[m], im[m]);
             __syncwarp();
+            // total is a multiple of 256 samples: pieces 0..7 (the lower sub-block) always exist, 8..15 iff the chunk is whole
+            longlong2 *dst = reinterpret_cast<longlong2 *>(p.out) + g0 + lane;
+            const longlong2 *src = sm + phys64(lane);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const longlong2 v = sm[phys64(lane) + 34u * j];          // phys64(lane + 32 j)
-                if (g0 + lane + 32u * j < p.total) reinterpret_cast<longlong2 *>(p.out)[g0 + lane + 32u * j] = v;
+            for (int j = 0; j < 8; ++j) dst[32 * j] = src[34 * j];       // phys64(lane + 32 j)
+            if (g0 + 512 <= p.total) {
+#pragma unroll
+                for (int j = 8; j < 16; ++j) dst[32 * j] = src[34 * j];
             }
         } else if (active) {
             if (p.out_sb == 8) {
