@@ -366,8 +366,12 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
         const bool full = g0 + 4096 <= p.total;
 
         auto prefetch_next = [&]() {                          // the next frame of this CTA
-            const long long nt = tile + gridDim.x;
-            if (tid == 0 && nt < p.n_tiles) {
+            // (the empty asm keeps the address / size arithmetic INSIDE thread 0's branch: left uniform, the front end
+            // hoists some twenty uniform-datapath instructions in front of it, and all eight warps issue them every frame)
+            long long nt = tile + gridDim.x;
+            if (tid != 0) return;
+            asm volatile("" : "+l"(nt));
+            if (nt < p.n_tiles) {
                 const long long left = p.total - (nt << 12);
                 const uint32_t bytes = (uint32_t)(left < 4096 ? left : 4096) * 4u;
                 if (NAT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> TMA writes

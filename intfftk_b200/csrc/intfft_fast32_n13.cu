@@ -38,6 +38,18 @@ constexpr unsigned kSmem13 = kHead32 + 2 * kTile8 * 8;   // table + exchange til
 // single-DSP limit only in their late stages: c5u runs STAGE 2..9 on the cheaper single-arrangement code)
 __device__ __forceinline__ unsigned pA_of(unsigned tid) { return phys8(16u * tid); }   // a thread's 16 contiguous tile slots
 
+struct TwPacked32 {       // {re:16 | im:16} of a twiddle pre-shifted by 16: re << 16 and im << 16 are a mask and a shift away
+    const int (&x)[15];
+    __device__ __forceinline__ void operator()(int w, int &wr, int &wi) const
+    {
+        wr = (int)((unsigned)x[w] & 0xffff0000u);
+        wi = (int)((unsigned)x[w] << 16);
+    }
+};
+#ifndef PACK_ROUND_C
+#define PACK_ROUND_C 1
+#endif
+
 template <bool DIT, int MODE, int KIND, int KLO>
 __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_constant__ Fast32Params p)
 {
@@ -59,14 +71,22 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
         const int j = w - ((1 << q) - 1);
         midtw[w * 16 + lo4] = __ldg(p.tw + (1u << (4 + q)) + lo4 + ((unsigned)j << 4));
     }
-    int uwr[15], uwi[15];                              // round C: index tid + 256 j at STAGE 8 + q
+    // round C: index tid + 256 j at STAGE 8 + q.  KIND_SINGLE_PRE (TWDL_WIDTH <= 16, twiddles pre-shifted by 16): both
+    // halves of a twiddle share ONE register, {re:16 | im:16}, and are split where they are used (LOP3 + SHF on the
+    // ALU port, which this multiply-bound kernel leaves half idle): 15 registers instead of 30, no spill to local memory
+    constexpr bool PACKC = KIND == KIND_SINGLE_PRE && PACK_ROUND_C;
+    int uwr[15], uwi[PACKC ? 1 : 15];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int j = 0; j < (1 << q); ++j) {
             const int2 w = __ldg(p.tw + (1u << (8 + q)) + tid + ((unsigned)j << 8));
-            uwr[(1 << q) - 1 + j] = w.x;
-            uwi[(1 << q) - 1 + j] = w.y;
+            if (PACKC) {
+                uwr[(1 << q) - 1 + j] = (int)(((unsigned)w.x & 0xffff0000u) | ((unsigned)w.y >> 16));
+            } else {
+                uwr[(1 << q) - 1 + j] = w.x;
+                uwi[PACKC ? 0 : (1 << q) - 1 + j] = w.y;
+            }
         }
     int lwr[15], lwi[15];
 #pragma unroll
@@ -191,7 +211,8 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
                 __syncthreads();                           // the tile may be rewritten once every thread has read it
                 // the tile is idle until the next frame's A -> B change: land that frame's lower half in it
                 if (h == 1 && tile + gridDim.x < p.n_tiles) prefetch(P, (tile + gridDim.x) << 13);
-                round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
+                if constexpr (PACKC) round32<4, DIT, MODE, KIND>(re, im, p, 8, TwPacked32{uwr}, false, false);
+                else round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
             }
             // ---- STAGE 12 between the parked lower half and the registers; coalesced stores ----
             auto stage12 = [&](auto out_sb_tag) {       // the container size is tested once per frame, not per store
@@ -221,7 +242,8 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
 #pragma unroll
                     for (int m = 0; m < 16; ++m) { const int2 v = S[m * 256 + tid]; re[m] = mk(v.x); im[m] = mk(v.y); }
                 }
-                round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
+                if constexpr (PACKC) round32<4, DIT, MODE, KIND>(re, im, p, 8, TwPacked32{uwr}, false, false);
+                else round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
                 __syncthreads();                           // every warp is done with the previous half's A-side reads
 #pragma unroll
                 for (int m = 0; m < 16; ++m) Q[pC + 288u * m] = make_int2(re[m].f, im[m].f);
