@@ -336,6 +336,17 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
     const bool tid_odd = tid & 1u;
     const int esz = 2 * p.in_sb;                                             // bytes per complex sample read
 
+    // DIF, three rounds: the tile lands as ONE bulk TMA copy (cp.async.bulk + mbarrier, dense, read at stride 256) instead
+    // of 16 element-sized cp.async per thread; the next tile's copy is issued behind the tile's first CTA barrier, when
+    // every thread has drained the landing area (single-buffered, like the packed-16 NAT variant)
+    constexpr bool TMAIN = !DIT && NR == 3;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    unsigned tma_phase = 0;
+    if (TMAIN) {
+        if (tid == 0) { tma::mbar_init(bar, 1); tma::mbar_fence_init(); }
+        __syncthreads();
+    }
+
     // first-round ownership (the same for every tile): local index of register m
     constexpr int RF = DIT ? 0 : NR - 1;                                      // first round processed
     constexpr int LOF = RF == 0 ? 0 : R0 + 4 * (RF - 1);
@@ -355,6 +366,16 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
     const bool pieces = (DIT || NR == 1) && (R0 == 4 || p.in_sb == 4);   // (a one-round DIF starts in the lowest round too)
     int2 *land = reinterpret_cast<int2 *>(stage);
     auto prefetch = [&](long long t) {
+        if (TMAIN) {
+            if (tid == 0) {
+                const unsigned bytes = 4096u * esz;
+                tma::mbar_expect_tx(bar, bytes);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(tma::smem_u32(stage)), "l"(reinterpret_cast<const char *>(p.in) + (t << 12) * esz), "r"(bytes),
+                               "r"(tma::smem_u32(bar)) : "memory");
+            }
+            return;
+        }
         const char *src = reinterpret_cast<const char *>(p.in) + ((t << 12) + basef) * esz;
         if (pieces) {
             const char *wsrc = reinterpret_cast<const char *>(p.in) + ((t << 12) + (wbase << 4)) * esz + 16u * lane;
@@ -429,7 +450,28 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
             const unsigned base = (tid & ((1u << lo) - 1u)) | ((tid >> lo) << (lo + R));
             const unsigned pbase = phys8(base);
 
-            if (first && staged) {                    // this tile was prefetched into the thread's slots
+            if (TMAIN && first && staged) {           // this tile was landed by the TMA engine: dense, element base + off
+                tma::mbar_wait(bar, tma_phase);
+                tma_phase ^= 1u;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned e = base + (((unsigned)(m & ((1 << R) - 1)) << lo) | ((unsigned)(m >> R) << (8 + R)));
+                    int a, b;
+                    if (p.in_sb == 2) {
+                        const unsigned x = reinterpret_cast<const unsigned *>(stage)[e];
+                        a = (int)(short)(x & 0xffffu);
+                        b = (int)x >> 16;
+                    } else {
+                        const int2 v = reinterpret_cast<const int2 *>(stage)[e];
+                        a = v.x;
+                        b = v.y;
+                    }
+                    if (p.in_wrap) { a = sx(a, p.dw); b = sx(b, p.dw); }
+                    re[m] = mk(a);
+                    im[m] = mk(b);
+                }
+                staged = false;                       // (re-armed behind the first barrier below)
+            } else if (first && staged) {             // this tile was prefetched into the thread's slots
                 cp_async_wait_all();
                 if (pieces) {
                     __syncwarp();                          // the other lanes' pieces of this warp's block have landed too
@@ -553,6 +595,11 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
                 const bool warp_local = (NR == 3 && R0 == 4) && ((DIT && rr == 0) || (!DIT && rr == 1));
                 if (warp_local) __syncwarp();
                 else __syncthreads();
+                if (TMAIN && rr == 0) {               // every thread has drained the landing area: next tile, if whole
+                    const long long nt = tile + gridDim.x;
+                    staged = nt < p.n_tiles && ((nt + 1) << 12) <= p.total;
+                    if (staged) prefetch(nt);
+                }
             }
         }
     }
