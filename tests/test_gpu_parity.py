@@ -665,3 +665,37 @@ def test_strided_tma_equals_cp_async_form(ib, oracle, kw, monkeypatch):
         assert torch.equal(a, b), (kw, direction)
         want = oracle.batch(oracle.generics(*og_args, direction), x, 0)
         assert np.array_equal(b.cpu().numpy(), want), (kw, direction)
+
+
+# ---- BASELINE c3 / c4 / c5 at their FULL sizes: sampled frames bit-exact against the oracle, and the exact
+# ---- size-independent property of this path — frames are independent, so the whole-batch result must equal the
+# ---- results of the two half-batches run through separate plans (different work splits, same integers)
+@pytest.mark.parametrize("name,kw,direction,batch", [
+    ("c3", dict(NFFT=16, DATA_WIDTH=24, FORMAT=1), 0, 4096),
+    ("c4", dict(NFFT=20, DATA_WIDTH=16, FORMAT=0), 0, 256),
+    ("c5", dict(NFFT=13, DATA_WIDTH=18, FORMAT=0), 1, 131072),
+    ("c5u", dict(NFFT=13, DATA_WIDTH=18, FORMAT=1), 1, 131072),
+])
+def test_full_size_baseline_configs(ib, oracle, name, kw, direction, batch):
+    g = ib.Generics(**kw)
+    n = 1 << g.NFFT
+    core = ib.Core(g, batch, direction)
+    x = core.new_input()
+    ib.fill_random(x, g.DATA_WIDTH, 0x696E7466 + len(name))
+    y = core.exec(x)
+    # (1) sampled frames: first, last, and a few inside
+    idx = sorted({0, 1, batch // 3, batch // 2, batch - 2, batch - 1})
+    sel = torch.tensor(idx, device=x.device)
+    hx = x.index_select(0, sel).cpu().numpy()
+    og = oracle.generics(g.NFFT, g.DATA_WIDTH, g.TWDL_WIDTH, g.FORMAT, g.RNDMODE, 1, 1, direction)
+    assert np.array_equal(y.index_select(0, sel).cpu().numpy(), oracle.batch(og, hx, 0)), name
+    # (2) frame independence at full size: two half-batch plans reproduce the whole-batch output bit for bit
+    half = batch // 2
+    lo, hi = ib.Core(g, half, direction), ib.Core(g, batch - half, direction)
+    y2 = torch.empty_like(y)
+    lo.exec(x[:half], y2[:half])
+    hi.exec(x[half:], y2[half:])
+    assert ib.checksum(y2) == ib.checksum(y), name
+    assert torch.equal(y2[half - 1:half + 1], y[half - 1:half + 1]), name
+    for c in (core, lo, hi):
+        c.close()
