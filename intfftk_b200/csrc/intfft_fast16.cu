@@ -1221,12 +1221,17 @@ int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw
     // G = 8: the TMA-staged variant (INTFFT_STRIDED_TMA=0 keeps the cp.async / STG one)
     const char *tma_env = std::getenv("INTFFT_STRIDED_TMA");
     const bool tma_now = !(tma_env && tma_env[0] == '0');
+    e = cudaErrorNotSupported;
     if (tma_now && G == 8) {
         if (!dit) e = dw16 ? launch_strided_tma_k<8, false, true>(p, mode, (int)grid, st) : launch_strided_tma_k<8, false, false>(p, mode, (int)grid, st);
         else e = dw16 ? launch_strided_tma_k<8, true, true>(p, mode, (int)grid, st) : launch_strided_tma_k<8, true, false>(p, mode, (int)grid, st);
     } else if (tma_now && G == 4) {
         if (!dit) e = dw16 ? launch_strided_tma_k<4, false, true>(p, mode, (int)grid, st) : launch_strided_tma_k<4, false, false>(p, mode, (int)grid, st);
         else e = dw16 ? launch_strided_tma_k<4, true, true>(p, mode, (int)grid, st) : launch_strided_tma_k<4, true, false>(p, mode, (int)grid, st);
+    }
+    if (e != cudaErrorNotSupported) {
+        // launched (or failed for a real reason) on the TMA-staged kernel; cudaErrorNotSupported = no tensor map could be
+        // encoded (driver without cuTensorMapEncodeTiled): the cp.async / STG kernels below do the same work
     } else if (G == 4) {
         if (!dit) e = dw16 ? launch_strided_k<4, false, true>(p, mode, (int)grid, st) : launch_strided_k<4, false, false>(p, mode, (int)grid, st);
         else e = dw16 ? launch_strided_k<4, true, true>(p, mode, (int)grid, st) : launch_strided_k<4, true, false>(p, mode, (int)grid, st);

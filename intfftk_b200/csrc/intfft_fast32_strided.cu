@@ -10,12 +10,17 @@ int f32_launch_strided(const f32::Fast32Params &p, int g, bool dit, int mode, in
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const char *tma_env = std::getenv("INTFFT_STRIDED_TMA");              // =0: the cp.async / STG form
     const bool use_tma = !(tma_env && tma_env[0] == '0');
+    // cudaErrorNotSupported from the TMA launchers = no tensor map could be encoded: the cp.async / STG kernels do the same work
     if (g == 4) {
-        if (use_tma) return (int)(dit ? f32::launch_strided_tma<4, true>(p, mode, kind, grid, st) : f32::launch_strided_tma<4, false>(p, mode, kind, grid, st));
+        cudaError_t e = cudaErrorNotSupported;
+        if (use_tma) e = dit ? f32::launch_strided_tma<4, true>(p, mode, kind, grid, st) : f32::launch_strided_tma<4, false>(p, mode, kind, grid, st);
+        if (e != cudaErrorNotSupported) return (int)e;
         return (int)(dit ? f32::launch_strided<4, true>(p, mode, kind, grid, st) : f32::launch_strided<4, false>(p, mode, kind, grid, st));
     }
     if (g == 8) {
-        if (use_tma) return (int)(dit ? f32::launch_strided_tma<8, true>(p, mode, kind, grid, st) : f32::launch_strided_tma<8, false>(p, mode, kind, grid, st));
+        cudaError_t e = cudaErrorNotSupported;
+        if (use_tma) e = dit ? f32::launch_strided_tma<8, true>(p, mode, kind, grid, st) : f32::launch_strided_tma<8, false>(p, mode, kind, grid, st);
+        if (e != cudaErrorNotSupported) return (int)e;
         return (int)(dit ? f32::launch_strided<8, true>(p, mode, kind, grid, st) : f32::launch_strided<8, false>(p, mode, kind, grid, st));
     }
     return (int)cudaErrorInvalidValue;
