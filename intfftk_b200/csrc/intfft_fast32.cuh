@@ -336,10 +336,10 @@ __global__ void __launch_bounds__(256, 2) fast32_kernel(const __grid_constant__ 
     const bool tid_odd = tid & 1u;
     const int esz = 2 * p.in_sb;                                             // bytes per complex sample read
 
-    // DIF, three rounds: the tile lands as ONE bulk TMA copy (cp.async.bulk + mbarrier, dense, read at stride 256) instead
+    // DIF, two or three rounds: the tile lands as ONE bulk TMA copy (cp.async.bulk + mbarrier, dense, read at stride 256) instead
     // of 16 element-sized cp.async per thread; the next tile's copy is issued behind the tile's first CTA barrier, when
     // every thread has drained the landing area (single-buffered, like the packed-16 NAT variant)
-    constexpr bool TMAIN = !DIT && NR == 3;
+    constexpr bool TMAIN = !DIT && NR >= 2;      // (a one-round DIF has no CTA barrier to issue the next copy behind)
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     unsigned tma_phase = 0;
     if (TMAIN) {
