@@ -160,11 +160,14 @@ __device__ __forceinline__ void cmul32(int dr, int di, int wr, int wi, const Cmu
 __device__ __forceinline__ int sra1(int x) { int r; asm("shr.s32 %0, %1, 1;" : "=r"(r) : "r"(x)); return r; }
 __device__ __forceinline__ int msub2(int t, int x) { int r; asm("mad.lo.s32 %0, %1, -2, %2;" : "=r"(r) : "r"(t), "r"(x)); return r; }
 
-template <int MODE> __device__ __forceinline__ void addsub32(const V &a, const V &b, int ow, V &x, V &y)
+// a_half: the A operand is the product of a multiplying stage of this round (DIF only), whose floor-half is what the
+// pre-shifted multiplier delivers directly — reading a.h then spares the product's full-value slice (a funnel shift and
+// a sign extension) that sra1(a.f) would drag in.  Resolved at compile time at every call site.
+template <int MODE> __device__ __forceinline__ void addsub32(const V &a, const V &b, int ow, V &x, V &y, bool a_half = false)
 {
     int xf, yf;
     if (MODE == MODE_TRUNC) {                   // (A>>1) + (B>>1) as one shift-add; (A>>1) - (B>>1) = sum - 2 (B>>1)
-        xf = sra1(a.f) + b.h;                   // so only the B operand's half is ever materialised
+        xf = (a_half ? a.h : sra1(a.f)) + b.h;  // so only the B operand's half is ever materialised
         yf = msub2(b.h, xf);                    // (as two subtractions ptxas re-balances the ports itself: IMAD.IADD for the
                                                 // adds, separate shifts instead of LEA.HI — 13 % more instructions; measured r02)
     } else if (MODE == MODE_ROUND) {            // (v >> 1) + v(0) == (v + 1) >> 1
@@ -184,12 +187,12 @@ template <int MODE> __device__ __forceinline__ void addsub32(const V &a, const V
 // forms are not even compiled in and the butterflies of a round form one basic block
 template <bool DIT, int MODE, int KIND, bool MUL = false>
 __device__ __forceinline__ void fly32(const Stg &st, bool odd, const CmultConsts &cm, V &ar, V &ai, V &br, V &bi,
-                                      int wr, int wi)
+                                      int wr, int wi, bool a_half = false)
 {
     if (!DIT) {
         V xr, xi, sr, si;
-        addsub32<MODE>(ar, br, st.ow, xr, sr);
-        addsub32<MODE>(ai, bi, st.ow, xi, si);
+        addsub32<MODE>(ar, br, st.ow, xr, sr, a_half);
+        addsub32<MODE>(ai, bi, st.ow, xi, si, a_half);
         ar = xr;
         ai = xi;
         if (!MUL && st.s == 0) {
@@ -296,7 +299,10 @@ __device__ __forceinline__ void round32(V (&re)[16], V (&im)[16], const Fast32Pa
             int wr = 0, wi = 0;
             if (MUL || st.s >= 2) tw(w, wr, wi);
             const bool odd = lo_is_zero ? ((m & 1) != 0) : tid_odd;
-            fly32<DIT, MODE, KIND, MUL>(st, odd, p.cm, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi);
+            // DIF: the pair (m, m | 1 << q) holds the PRODUCTS of the round's previous step iff bit q + 1 of m is set
+            // (and that step multiplied: STAGE >= 2)
+            const bool a_half = !DIT && KIND == KIND_SINGLE_PRE && step > 0 && (m & (2 << q)) != 0 && (MUL || s0 + q + 1 >= 2);
+            fly32<DIT, MODE, KIND, MUL>(st, odd, p.cm, re[m], im[m], re[m | (1 << q)], im[m | (1 << q)], wr, wi, a_half);
         }
     }
 }
@@ -899,9 +905,7 @@ template <int G, typename K> cudaError_t launch_any_tma(K k, const Fast32Params 
 }
 template <int G, bool DIT> cudaError_t launch_strided_tma(const Fast32Params &p, int mode, int kind, int grid, cudaStream_t st)
 {
-    if constexpr (DIT) {
-        if (kind == KIND_SINGLE_PRE) return launch_any_tma<G>(fast32_strided_tma_kernel<G, DIT, MODE_TRUNC, KIND_SINGLE_PRE>, p, grid, st);
-    }
+    if (kind == KIND_SINGLE_PRE) return launch_any_tma<G>(fast32_strided_tma_kernel<G, DIT, MODE_TRUNC, KIND_SINGLE_PRE>, p, grid, st);
     switch (mode * 2 + kind) {
     case MODE_TRUNC * 2 + 0: return launch_any_tma<G>(fast32_strided_tma_kernel<G, DIT, MODE_TRUNC, KIND_SINGLE>, p, grid, st);
     case MODE_TRUNC * 2 + 1: return launch_any_tma<G>(fast32_strided_tma_kernel<G, DIT, MODE_TRUNC, KIND_MIXED>, p, grid, st);
@@ -924,9 +928,8 @@ template <typename K> cudaError_t launch_any(K k, const Fast32Params &p, int gri
 // one translation unit per direction keeps the build parallel
 template <int NLOG2, bool DIT> cudaError_t launch_contig(const Fast32Params &p, int mode, int kind, int grid, cudaStream_t st)
 {
-    if constexpr (DIT) {         // TRUNCATE, every stage single-DSP, pre-shifted twiddles in p (launch_fast32)
-        if (kind == KIND_SINGLE_PRE) return launch_any(fast32_kernel<NLOG2, DIT, MODE_TRUNC, KIND_SINGLE_PRE>, p, grid, st);
-    }
+    // TRUNCATE, every stage single-DSP, pre-shifted twiddles in p (launch_fast32)
+    if (kind == KIND_SINGLE_PRE) return launch_any(fast32_kernel<NLOG2, DIT, MODE_TRUNC, KIND_SINGLE_PRE>, p, grid, st);
     switch (mode * 2 + kind) {
     case MODE_TRUNC * 2 + 0: return launch_any(fast32_kernel<NLOG2, DIT, MODE_TRUNC, KIND_SINGLE>, p, grid, st);
     case MODE_TRUNC * 2 + 1: return launch_any(fast32_kernel<NLOG2, DIT, MODE_TRUNC, KIND_MIXED>, p, grid, st);
@@ -954,9 +957,7 @@ template <bool DIT> cudaError_t launch_contig_n(const Fast32Params &p, int bits,
 }
 template <int G, bool DIT> cudaError_t launch_strided(const Fast32Params &p, int mode, int kind, int grid, cudaStream_t st)
 {
-    if constexpr (DIT) {
-        if (kind == KIND_SINGLE_PRE) return launch_any(fast32_strided_kernel<G, DIT, MODE_TRUNC, KIND_SINGLE_PRE>, p, grid, st);
-    }
+    if (kind == KIND_SINGLE_PRE) return launch_any(fast32_strided_kernel<G, DIT, MODE_TRUNC, KIND_SINGLE_PRE>, p, grid, st);
     switch (mode * 2 + kind) {
     case MODE_TRUNC * 2 + 0: return launch_any(fast32_strided_kernel<G, DIT, MODE_TRUNC, KIND_SINGLE>, p, grid, st);
     case MODE_TRUNC * 2 + 1: return launch_any(fast32_strided_kernel<G, DIT, MODE_TRUNC, KIND_MIXED>, p, grid, st);

@@ -297,7 +297,7 @@ template <bool DIT> cudaError_t launch_n13_dir(const Fast32Params &p, int mode, 
     constexpr int S = KIND_SINGLE, M = KIND_MIXED;
     // DIT, TRUNCATE, every stage single-DSP (BASELINE c5): the pre-shifted-twiddle instance; the caller has put the
     // pre-shifted table / lowest-round twiddles into p (intfft_fast32_strided.cu: launch_fast32)
-    if (DIT && kind == KIND_SINGLE_PRE) return launch_n13(fast32_n13_kernel<DIT, MODE_TRUNC, KIND_SINGLE_PRE, KIND_SINGLE_PRE>, p, grid, st);
+    if (kind == KIND_SINGLE_PRE) return launch_n13(fast32_n13_kernel<DIT, MODE_TRUNC, KIND_SINGLE_PRE, KIND_SINGLE_PRE>, p, grid, st);
     switch (mode * 4 + kind * 2 + klo) {
     case MODE_TRUNC * 4 + 0: return launch_n13(fast32_n13_kernel<DIT, MODE_TRUNC, S, S>, p, grid, st);
     case MODE_TRUNC * 4 + 2: return launch_n13(fast32_n13_kernel<DIT, MODE_TRUNC, M, S>, p, grid, st);

@@ -71,7 +71,7 @@ int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const 
     long long grid = 2ll * num_sms;
     int e = (int)cudaErrorInvalidValue;
     // DIT, TRUNCATE, every stage of the pass single-DSP, TWDL_WIDTH < 19: the pre-shifted-twiddle instances
-    const bool pre = dit && mode == MODE_TRUNC && kind == f32::KIND_SINGLE && twp && !std::getenv("INTFFT_NO_PRESHIFT");
+    const bool pre = mode == MODE_TRUNC && kind == f32::KIND_SINGLE && twp && !std::getenv("INTFFT_NO_PRESHIFT");
     if (pre && !(pd.kp.c == 0 && pd.kp.g == 13)) {
         p.tw = twp;
         for (int i = 0; i < 16; ++i) { p.lw_r[i] = lwp_r[i]; p.lw_i[i] = lwp_i[i]; }
@@ -82,7 +82,7 @@ int launch_fast32(const PassDesc &pd, int mode, bool dit, const int2 *tw, const 
         grid = 3ll * num_sms;                          // 80 registers, 70 KB of shared memory: three CTAs per SM
         if (grid > p.n_tiles) grid = p.n_tiles;
         if (grid < 1) grid = 1;
-        if (dit && mode == MODE_TRUNC && kind == f32::KIND_SINGLE && twp && tw16 && !std::getenv("INTFFT_NO_PRESHIFT")) {
+        if (mode == MODE_TRUNC && kind == f32::KIND_SINGLE && twp && tw16 && !std::getenv("INTFFT_NO_PRESHIFT")) {
             p.tw = twp;
             p.tw16 = tw16;
             for (int i = 0; i < 16; ++i) { p.lw_r[i] = lwp_r[i]; p.lw_i[i] = lwp_i[i]; }
