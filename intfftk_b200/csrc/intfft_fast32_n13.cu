@@ -132,10 +132,12 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
         }
         cp_async_commit();
     };
-    if (DIT && (long long)blockIdx.x < p.n_tiles) prefetch(P, (long long)blockIdx.x << 13);
+    // frame counters are 32-bit (at most 2^27 frames): the kernel runs at its register cap, 64-bit ones cost spills
+    const unsigned n_frames = (unsigned)p.n_tiles;
+    if (DIT && blockIdx.x < n_frames) prefetch(P, (long long)blockIdx.x << 13);
 
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const long long g0 = tile << 13;
+    for (unsigned tile = blockIdx.x; tile < n_frames; tile += gridDim.x) {
+        const long long g0 = (long long)tile << 13;
         V re[16], im[16];
 
         if (!DIT) {
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
                 for (int m = 0; m < 16; ++m) { const int2 v = Q[pC + 288u * m]; re[m] = mk(v.x); im[m] = mk(v.y); }
                 __syncthreads();                           // the tile may be rewritten once every thread has read it
                 // the tile is idle until the next frame's A -> B change: land that frame's lower half in it
-                if (h == 1 && tile + gridDim.x < p.n_tiles) prefetch(P, (tile + gridDim.x) << 13);
+                if (h == 1 && tile + gridDim.x < n_frames) prefetch(P, (long long)(tile + gridDim.x) << 13);
                 if constexpr (PACKC) round32<4, DIT, MODE, KIND>(re, im, p, 8, TwPacked32{uwr}, false, false);
                 else round32<4, DIT, MODE, KIND>(re, im, p, 8, TwRegs32{uwr, uwi}, false, false);
             }

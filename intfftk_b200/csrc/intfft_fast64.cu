@@ -342,8 +342,8 @@ __global__ void __launch_bounds__(256, 2) fast64_kernel(const __grid_constant__ 
     constexpr bool pf = PF;                            // in_sb == 4 (the launcher sized the landing area)
     int2 *land = reinterpret_cast<int2 *>(smem_raw + 8 * kWarpSlots * 16) + warp * kLandElems;
     // piece q = lane + 32 j holds samples 2q, 2q + 1: physL(2 lane + 64 j) = physL(2 lane) + 72 j
-    auto prefetch = [&](int64_t chunk) {
-        const int64_t g = chunk << 9;
+    auto prefetch = [&](unsigned chunk) {
+        const int64_t g = (int64_t)chunk << 9;
         const char *src = reinterpret_cast<const char *>(p.in) + g * 8 + 16u * lane;
         int2 *dst = land + physL(2u * lane);
         if (g + 512 <= p.total) {                      // whole chunk (all but possibly the last one): no predicates
@@ -357,10 +357,13 @@ __global__ void __launch_bounds__(256, 2) fast64_kernel(const __grid_constant__ 
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (pf && (int64_t)blockIdx.x * 8 + warp < p.n_chunks) prefetch((int64_t)blockIdx.x * 8 + warp);
+    // chunk counters are 32-bit (total <= 2^40 samples = 2^31 chunks): the 64-bit ones were spilled to local memory and
+    // the loop test waited on their reload every chunk
+    const unsigned n_chunks = (unsigned)p.n_chunks, chunk_step = gridDim.x * 8u;
+    if (pf && blockIdx.x * 8u + warp < n_chunks) prefetch(blockIdx.x * 8u + warp);
 
-    for (int64_t chunk = (int64_t)blockIdx.x * 8 + warp; chunk < p.n_chunks; chunk += (int64_t)gridDim.x * 8) {
-        const int64_t g0 = chunk << 9;
+    for (unsigned chunk = blockIdx.x * 8u + warp; chunk < n_chunks; chunk += chunk_step) {
+        const int64_t g0 = (int64_t)chunk << 9;
         const bool active = g0 + sub * 256 < p.total;
         int64_t re[16], im[16];
         // ---- first round: from the landing area (prefetched one chunk ago) or straight from HBM ----
@@ -384,8 +387,8 @@ __global__ void __launch_bounds__(256, 2) fast64_kernel(const __grid_constant__ 
                 }
             }
             __syncwarp();                              // every lane has drained the area
-            const int64_t next = chunk + (int64_t)gridDim.x * 8;
-            if (next < p.n_chunks) prefetch(next);
+            const unsigned next = chunk + chunk_step;
+            if (next < n_chunks && next > chunk) prefetch(next);
         } else if (p.in_sb == 4) {
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
