@@ -14,6 +14,12 @@ PLANS = {
     "u12": (65536, 0, dict(NFFT=12, DATA_WIDTH=16, FORMAT=1)),
     "r12": (65536, 0, dict(NFFT=12, DATA_WIDTH=16, FORMAT=0, RNDMODE=1)),
     "s16": (4096, 0, dict(NFFT=16, DATA_WIDTH=16, FORMAT=0)),
+    "d18": (32768, 0, dict(NFFT=12, DATA_WIDTH=18, FORMAT=0)),
+    "t18": (32768, 1, dict(NFFT=12, DATA_WIDTH=18, FORMAT=0)),
+    "w12": (65536, 0, dict(NFFT=12, DATA_WIDTH=12, FORMAT=0)),
+    "n13": (32768, 0, dict(NFFT=13, DATA_WIDTH=16, FORMAT=0)),
+    "n13t": (32768, 1, dict(NFFT=13, DATA_WIDTH=16, FORMAT=0)),
+    "n10": (262144, 0, dict(NFFT=10, DATA_WIDTH=16, FORMAT=0)),
 }
 for name in sys.argv[1:]:
     batch, direction, gk = PLANS[name]
