@@ -102,6 +102,8 @@ void build_passes(Plan &pl)
         else           { spans.push_back({0, 8, false}); spans.push_back({8, n - 8, true}); }
     } else if ((f32 || f16) && n == 13 && !std::getenv("INTFFT_N13_TWO_PASS")) {
         spans.push_back({0, 13, false});              // one-pass 8192-point kernels (intfft_fast32_n13.cu, fast16_n13_kernel)
+    } else if (f16 && n == 14 && !std::getenv("INTFFT_N14_TWO_PASS")) {
+        spans.push_back({0, 14, false});              // one-pass 16384-point packed-16 kernel (fast16_n14_kernel)
     } else if ((f16 || f32) && n >= 13) {
         // packed-16 kernels: top 4 or 8 bits as a strided pass, the rest (9..12 bits) contiguous
         const int g_hi = n <= 16 ? 4 : 8, g_lo = n - g_hi;
@@ -122,7 +124,7 @@ void build_passes(Plan &pl)
         PassDesc pd{};
         PassParams &kp = pd.kp;
         kp.n = n;
-        kp.L = (!wide8 && !sp.strided && n == 13 && sp.bits == 13) ? 13 : 12;
+        kp.L = (!wide8 && !sp.strided && (n == 13 || n == 14) && sp.bits == n) ? n : 12;
         kp.g = sp.bits;
         kp.pb = sp.lo_bit;
         kp.c = sp.strided ? kp.L - sp.bits : 0;
@@ -403,7 +405,8 @@ static int run_pass(const intfft_plan *p, size_t i, const void *in, void *out, l
     int e;
     if (pd.path == 1)
         e = pd.kp.c > 0 ? launch_fast16_strided(pd, p->mode, dit, p->d_twp, p->num_sms, cuda_stream, &p->tay16)
-            : (pd.kp.g == 13 ? launch_fast16_n13(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream)
+            : (pd.kp.g == 14 ? launch_fast16_n14(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream)
+               : pd.kp.g == 13 ? launch_fast16_n13(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream)
                              : launch_fast16(pd, p->mode, dit, p->d_twp, p->lw_r, p->lw_i, p->num_sms, cuda_stream));
     else if (pd.path == 2)
         e = launch_fast32(pd, p->mode, dit, p->d_tw, p->lw32_r, p->lw32_i, p->num_sms, cuda_stream, p->d_twp32,
@@ -889,7 +892,7 @@ int intfft_describe(const intfft_generics *g, int64_t batch, char *buf, size_t l
             const bool strided = kp.c > 0;
             const char *fam = "tile";
             char extra[48] = "";
-            if (pd.path == 1) fam = strided ? "fast16_strided" : (kp.g == 13 ? "fast16_n13" : "fast16");
+            if (pd.path == 1) fam = strided ? "fast16_strided" : (kp.g == 14 ? "fast16_n14" : kp.g == 13 ? "fast16_n13" : "fast16");
             else if (pd.path == 2) fam = strided ? "fast32_strided" : (kp.g == 13 ? "fast32_n13" : "fast32");
             else if (pd.path == 3) { fam = "fast64"; std::snprintf(extra, sizeof extra, ", instance %d", fast64_uniform_kind(kp, dit)); }
             else if (pd.path == 4) fam = "fast64_strided";

@@ -670,12 +670,13 @@ __global__ void __launch_bounds__(256, 3) fast16_n13_kernel(const __grid_constan
                 for (int m = 0; m < 16; ++m)
                     sm[pC + phys((unsigned)m << 8)] = (RAW && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632) : pack(re[m], im[m]);
                 __syncthreads();
-                // every thread has read the landing buffer (its STAGE-12 operands and, in the upper block, its own
-                // product slots): the next frame may land
-                if (blk == 1 && tid == 0 && frame + gridDim.x < n_frames) {
+                // every thread has read block blk of the landing buffer (its STAGE-12 operands and, in the upper block,
+                // its own product slots): that half of the NEXT frame may land — two 16 KB copies on one barrier, the
+                // first one issued while the upper block of this frame is still being computed
+                if (tid == 0 && frame + gridDim.x < n_frames) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic stores -> TMA writes
-                    mbar_expect_tx(&bar[0], 32768u);
-                    tma_load_1d(stage[0], p.in + ((frame + gridDim.x) << 13), 32768u, &bar[0]);
+                    if (blk == 0) mbar_expect_tx(&bar[0], 32768u);
+                    tma_load_1d(stage[blk], p.in + ((frame + gridDim.x) << 13) + 4096 * blk, 16384u, &bar[0]);
                 }
                 // round 1: STAGE 7..4 (stride 16)
 #pragma unroll
@@ -774,6 +775,245 @@ cudaError_t launch_n13_k(const Fast16Params &p, int mode, int grid, cudaStream_t
 {
     const int smem = kSmemHead + 2 * kTileWords * 4 + (DIT ? (int)kTileWords * 4 : 2 * 4096 * 4);
     auto k = mode == MODE_ROUND ? fast16_n13_kernel<DIT, DW16, MODE_ROUND> : fast16_n13_kernel<DIT, DW16, MODE_TRUNC>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-pass 16384-point packed-16 kernel (NFFT = 14, 16-bit scaled): the fast16_n13 pattern with FOUR 4096-sample
+// blocks per frame.  It replaces the strided-4 + contiguous-10 schedule, whose strided pass does four stages at the
+// price of a whole HBM round trip (2.1 GB in 0.34 ms = 6.2 TB/s: that pass runs AT the memory roofline).
+// STAGE 13 pairs block b with b + 2, STAGE 12 block 2c with 2c + 1; in the top round's ownership (tid + 256 m) all four
+// samples of such a radix-4 group belong to the SAME thread, so both stages need no exchange:
+//   DIF: the frame lands as ONE 64 KB TMA bulk copy; STAGE 13 / 12 run straight out of the landing buffer — block 0's
+//        results stay in registers, the other three go back into the thread's own slots, from where blocks 1..3 are
+//        read like TMA-landed tiles.  The next frame's copy is issued once block 3 has been read (single-buffered).
+//   DIT: blocks 0..2 park their top-round results in thread-private slots; after block 3 STAGE 12 / 13 run between the
+//        parked blocks and the registers and the whole frame leaves as warp-coalesced 128-byte stores.
+// 105 / 88 KB of shared memory: two CTAs per SM.  Twiddles of STAGE 12 / 13: three per radix-4 group, through L1 / L2.
+template <bool DIT, bool DW16, int MODE>
+__global__ void __launch_bounds__(256, 2) fast16_n14_kernel(const __grid_constant__ Fast16Params p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    int2 *midtw = reinterpret_cast<int2 *>(smem_raw + 128);
+    uint32_t(*work)[kTileWords] = reinterpret_cast<uint32_t(*)[kTileWords]>(smem_raw + kSmemHead);
+    uint32_t(*stage)[4096] = reinterpret_cast<uint32_t(*)[4096]>(smem_raw + kSmemHead + 2 * kTileWords * 4);   // DIF: 4 blocks
+    uint32_t *land = reinterpret_cast<uint32_t *>(smem_raw + kSmemHead + kTileWords * 4);                        // DIT
+    uint32_t(*park)[4096] = reinterpret_cast<uint32_t(*)[4096]>(smem_raw + kSmemHead + 2 * kTileWords * 4);     // DIT: 3 blocks
+
+    const unsigned tid = threadIdx.x;
+    const int sh_full = p.sh_full, sh_half = p.sh_half;
+    const bool tid_odd = tid & 1u;
+    const unsigned n_frames = (unsigned)p.n_tiles;   // frames of 16384 samples
+    constexpr bool RAW = !DIT && DW16;
+    auto warp_piece = [&](int c) {                   // 16-byte piece lane + 32 c of the warp's 512 contiguous samples
+        const unsigned q = (tid & 31u) + 32u * c;
+        return ((tid & ~31u) << 4) + 4u * q;
+    };
+
+    if (!DIT) {
+        if (tid == 0) {
+            mbar_init(&bar[0], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0 && blockIdx.x < n_frames) {
+            mbar_expect_tx(&bar[0], 65536u);
+            tma_load_1d(stage[0], p.in + ((long long)blockIdx.x << 14), 65536u, &bar[0]);
+        }
+    }
+    auto prefetch_warp = [&](long long block) {      // DIT: one 4096-sample block -> the skewed landing tile
+        const long long g = block << 12;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned i = warp_piece(j);
+            cp_async_16z(land + phys(i), p.in + g + i, 16u);
+        }
+        cp_async_commit_group();
+    };
+    if (DIT && blockIdx.x < n_frames) prefetch_warp((long long)blockIdx.x << 2);
+
+    // ---- batch-invariant twiddles: STAGE 4..7 table, STAGE 8..11 registers, STAGE 2..3 parameters ----
+    if (tid < 240) {
+        const int w = tid >> 4, lo4 = tid & 15;
+        const int q = w >= 7 ? 3 : (w >= 3 ? 2 : (w >= 1 ? 1 : 0));
+        const int j = w - ((1 << q) - 1);
+        midtw[w * 16 + lo4] = __ldg(p.twp + (1u << (4 + q)) + lo4 + ((unsigned)j << 4));
+    }
+    int uwr[15], uwi[15];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < (1 << q); ++j) {
+            const int2 w = __ldg(p.twp + (1u << (8 + q)) + tid + ((unsigned)j << 8));
+            uwr[(1 << q) - 1 + j] = w.x;
+            uwi[(1 << q) - 1 + j] = w.y;
+        }
+    int lwr[15], lwi[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) { lwr[i] = p.lw_r[i]; lwi[i] = p.lw_i[i]; }
+    const int2 *tw12 = p.twp + 4096 + tid;           // STAGE 12: index tid + 256 m
+    const int2 *tw13 = p.twp + 8192 + tid;           // STAGE 13: index tid + 256 m (+ 4096 for the odd blocks)
+    __syncthreads();
+
+    const unsigned pA = phys(16u * tid);                                    // round 0: 16 contiguous samples
+    const unsigned pB = phys((tid & 15u) | ((tid >> 4) << 8));              // round 1: stride 16
+    const unsigned pC = phys(tid);                                          // round 2: stride 256
+
+    unsigned it = 0;
+    for (unsigned frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++it) {
+        const long long g0 = (long long)frame << 14;
+        int re[16], im[16];
+
+        if (!DIT) {
+            // ---- STAGE 13 and 12 out of the landing buffer: block 0 -> registers, blocks 1..3 -> the thread's own slots ----
+            mbar_wait(&bar[0], it & 1);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const unsigned i = tid + 256 * m;
+                int r1, i1, r2, i2, r3, i3;
+                unpack<DW16>(stage[0][i], p.dw, re[m], im[m]);
+                unpack<DW16>(stage[1][i], p.dw, r1, i1);
+                unpack<DW16>(stage[2][i], p.dw, r2, i2);
+                unpack<DW16>(stage[3][i], p.dw, r3, i3);
+                const int2 wa = __ldg(tw13 + 256 * m), wb = __ldg(tw13 + 4096 + 256 * m), wc = __ldg(tw12 + 256 * m);
+                fly<false, DW16, MODE, false>(13, false, re[m], im[m], r2, i2, wa.x, wa.y, sh_full, sh_half);
+                fly<false, DW16, MODE, false>(13, false, r1, i1, r3, i3, wb.x, wb.y, sh_full, sh_half);
+                fly<false, DW16, MODE, RAW>(12, false, re[m], im[m], r1, i1, wc.x, wc.y, sh_full, sh_half);
+                fly<false, DW16, MODE, RAW>(12, false, r2, i2, r3, i3, wc.x, wc.y, sh_full, sh_half);
+                stage[1][i] = RAW ? __byte_perm((unsigned)r1, (unsigned)i1, 0x7632) : pack(r1, i1);
+                stage[2][i] = pack(r2, i2);
+                stage[3][i] = RAW ? __byte_perm((unsigned)r3, (unsigned)i3, 0x7632) : pack(r3, i3);
+            }
+#pragma unroll 1
+            for (int blk = 0; blk < 4; ++blk) {
+                uint32_t *sm = work[blk & 1];
+                if (blk) {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) unpack<true>(stage[blk][tid + 256 * m], p.dw, re[m], im[m]);
+                }
+                // round 2: STAGE 11..8 (stride 256)
+                round_regs<8, 4, false, DW16, MODE, RAW>(re, im, TwRegs{uwr, uwi}, tid_odd, sh_full, sh_half);
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+                    sm[pC + phys((unsigned)m << 8)] = (RAW && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632) : pack(re[m], im[m]);
+                __syncthreads();
+                // every thread has read block blk of the landing buffer (its STAGE 13 / 12 operands and, for blk > 0, its
+                // own slots): that quarter of the NEXT frame may land — four 16 KB copies on one barrier, the first
+                // three issued while later blocks of this frame are still being computed
+                if (tid == 0 && frame + gridDim.x < n_frames) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic stores -> TMA writes
+                    if (blk == 0) mbar_expect_tx(&bar[0], 65536u);
+                    tma_load_1d(stage[blk], p.in + ((long long)(frame + gridDim.x) << 14) + 4096 * blk, 16384u, &bar[0]);
+                }
+                // round 1: STAGE 7..4 (stride 16)
+#pragma unroll
+                for (int m = 0; m < 16; ++m) unpack<true>(sm[pB + phys((unsigned)m << 4)], p.dw, re[m], im[m]);
+                round_regs<4, 4, false, DW16, MODE, RAW>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+                    sm[pB + phys((unsigned)m << 4)] = (RAW && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632) : pack(re[m], im[m]);
+                __syncwarp();                                   // this hand-over stays inside the warp
+                // round 0: STAGE 3..0 (16 contiguous samples)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(sm + pA + phys(4 * c));
+                    unpack<true>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
+                    unpack<true>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
+                    unpack<true>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
+                    unpack<true>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                }
+                round_regs<0, 4, false, DW16, MODE, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4 *>(sm + pA + phys(4 * c)) =
+                        make_uint4(pack(re[4 * c], im[4 * c]), pack(re[4 * c + 1], im[4 * c + 1]),
+                                   pack(re[4 * c + 2], im[4 * c + 2]), pack(re[4 * c + 3], im[4 * c + 3]));
+                __syncwarp();
+                uint32_t *dst = p.out + g0 + 4096 * blk;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const unsigned i = warp_piece(c);
+                    *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(sm + phys(i));
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int blk = 0; blk < 4; ++blk) {
+                uint32_t *sm = work[0];
+                // round 0: STAGE 0..3 on the block the warp landed one block ago
+                cp_async_wait_group0();
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(land + pA + phys(4 * c));
+                    unpack<DW16>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
+                    unpack<DW16>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
+                    unpack<DW16>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
+                    unpack<DW16>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                }
+                __syncwarp();                                   // every lane has drained the warp's region
+                {
+                    const long long nb = blk < 3 ? 4ll * frame + blk + 1 : 4ll * (frame + gridDim.x);
+                    if (nb < 4ll * n_frames) prefetch_warp(nb);
+                }
+                round_regs<0, 4, true, DW16, MODE, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
+                // the exchange tile is single: the previous block's cross-warp reads of it must be complete before this
+                // block writes
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4 *>(sm + pA + phys(4 * c)) =
+                        make_uint4(pack(re[4 * c], im[4 * c]), pack(re[4 * c + 1], im[4 * c + 1]),
+                                   pack(re[4 * c + 2], im[4 * c + 2]), pack(re[4 * c + 3], im[4 * c + 3]));
+                __syncwarp();
+                // round 1: STAGE 4..7
+#pragma unroll
+                for (int m = 0; m < 16; ++m) unpack<true>(sm[pB + phys((unsigned)m << 4)], p.dw, re[m], im[m]);
+                round_regs<4, 4, true, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) sm[pB + phys((unsigned)m << 4)] = pack(re[m], im[m]);
+                __syncthreads();
+                // round 2: STAGE 8..11
+#pragma unroll
+                for (int m = 0; m < 16; ++m) unpack<true>(sm[pC + phys((unsigned)m << 8)], p.dw, re[m], im[m]);
+                round_regs<8, 4, true, DW16, MODE, false>(re, im, TwRegs{uwr, uwi}, tid_odd, sh_full, sh_half);
+                if (blk < 3) {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) park[blk][m * 256 + tid] = pack(re[m], im[m]);   // thread-private slots
+                } else {
+                    // ---- STAGE 12 then 13 between the three parked blocks and the registers; coalesced stores ----
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        int r0, i0, r1, i1, r2, i2;
+                        unpack<true>(park[0][m * 256 + tid], p.dw, r0, i0);
+                        unpack<true>(park[1][m * 256 + tid], p.dw, r1, i1);
+                        unpack<true>(park[2][m * 256 + tid], p.dw, r2, i2);
+                        const int2 wc = __ldg(tw12 + 256 * m), wa = __ldg(tw13 + 256 * m), wb = __ldg(tw13 + 4096 + 256 * m);
+                        fly<true, DW16, MODE>(12, false, r0, i0, r1, i1, wc.x, wc.y, sh_full, sh_half);
+                        fly<true, DW16, MODE>(12, false, r2, i2, re[m], im[m], wc.x, wc.y, sh_full, sh_half);
+                        fly<true, DW16, MODE>(13, false, r0, i0, r2, i2, wa.x, wa.y, sh_full, sh_half);
+                        fly<true, DW16, MODE>(13, false, r1, i1, re[m], im[m], wb.x, wb.y, sh_full, sh_half);
+                        uint32_t *dst = p.out + g0 + tid + 256 * m;
+                        dst[0] = pack(r0, i0);
+                        dst[4096] = pack(r1, i1);
+                        dst[8192] = pack(r2, i2);
+                        dst[12288] = pack(re[m], im[m]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <bool DIT, bool DW16>
+cudaError_t launch_n14_k(const Fast16Params &p, int mode, int grid, cudaStream_t st)
+{
+    const int smem = DIT ? (int)(kSmemHead + 2 * kTileWords * 4 + 3 * 4096 * 4) : (int)(kSmemHead + 2 * kTileWords * 4 + 4 * 4096 * 4);
+    auto k = mode == MODE_ROUND ? fast16_n14_kernel<DIT, DW16, MODE_ROUND> : fast16_n14_kernel<DIT, DW16, MODE_TRUNC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, smem, st>>>(p);
@@ -1282,6 +1522,32 @@ int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const
         break;
     default: e = cudaErrorInvalidValue; break;
     }
+    count_launch();
+    return (int)e;
+}
+
+// one-pass 16384-point packed-16 plan (kp.g == 14)
+int launch_fast16_n14(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
+                      int num_sms, void *stream)
+{
+    Fast16Params p{};
+    p.in = reinterpret_cast<const uint32_t *>(pd.kp.in);
+    p.out = reinterpret_cast<uint32_t *>(pd.kp.out);
+    p.twp = twp;
+    p.total = pd.kp.total;
+    p.n_tiles = pd.kp.total >> 14;                  // frames
+    p.dw = pd.kp.dw;
+    p.sh_full = 32 - p.dw;
+    p.sh_half = 33 - p.dw;
+    for (int i = 0; i < 16; ++i) { p.lw_r[i] = lw_r[i]; p.lw_i[i] = lw_i[i]; }
+    long long grid = 2ll * num_sms;
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    if (grid < 1) grid = 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool dw16 = p.dw == 16;
+    cudaError_t e;
+    if (!dit) e = dw16 ? launch_n14_k<false, true>(p, mode, (int)grid, st) : launch_n14_k<false, false>(p, mode, (int)grid, st);
+    else e = dw16 ? launch_n14_k<true, true>(p, mode, (int)grid, st) : launch_n14_k<true, false>(p, mode, (int)grid, st);
     count_launch();
     return (int)e;
 }

@@ -129,6 +129,8 @@ bool fast16_supported(const intfft_generics &g);
 bool fast16_pair_supported(const intfft_generics &g);
 int launch_fast16_n13(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
                       int num_sms, void *stream);
+int launch_fast16_n14(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
+                      int num_sms, void *stream);
 int launch_fast16_pair(const PassDesc &pd, int mode, const int2 *twp, const int *lw_r, const int *lw_i, int num_sms,
                        void *stream);
 int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *twp, int num_sms, void *stream,

@@ -109,7 +109,8 @@ PLAN_CHAINS = [
     (dict(NFFT=7, DATA_WIDTH=12, FORMAT=0, RNDMODE=1), 1, ["fast16[bits 0..6"]),
     (dict(NFFT=13, DATA_WIDTH=16, FORMAT=0), 0, ["fast16_n13[bits 0..12, 4->4 B]"]),            # one pass since round 2
     (dict(NFFT=13, DATA_WIDTH=12, FORMAT=0, RNDMODE=1), 1, ["fast16_n13[bits 0..12, 4->4 B]"]),
-    (dict(NFFT=14, DATA_WIDTH=16, FORMAT=0), 0, ["fast16_strided[bits 10..13", "fast16[bits 0..9"]),
+    (dict(NFFT=14, DATA_WIDTH=16, FORMAT=0), 0, ["fast16_n14[bits 0..13, 4->4 B]"]),            # one pass since round 2
+    (dict(NFFT=15, DATA_WIDTH=16, FORMAT=0), 0, ["fast16_strided[bits 11..14", "fast16[bits 0..10"]),
     (dict(NFFT=16, DATA_WIDTH=16, FORMAT=0), 1, ["fast16[bits 0..11", "fast16_strided[bits 12..15"]),
     (dict(NFFT=17, DATA_WIDTH=14, FORMAT=0), 0, ["fast16_strided[bits 9..16", "fast16[bits 0..8"]),
     # 32-bit lanes: wider data, wider twiddles, unscaled growth that still fits

@@ -699,3 +699,24 @@ def test_full_size_baseline_configs(ib, oracle, name, kw, direction, batch):
     assert torch.equal(y2[half - 1:half + 1], y[half - 1:half + 1]), name
     for c in (core, lo, hi):
         c.close()
+
+
+# ---- one-pass 8192- / 16384-point packed-16 kernels against the oracle AND against the two-pass schedule they replace ----
+@pytest.mark.parametrize("nfft,env", [(13, "INTFFT_N13_TWO_PASS"), (14, "INTFFT_N14_TWO_PASS")])
+@pytest.mark.parametrize("dw,rnd", [(16, 0), (12, 0), (16, 1), (9, 1)])
+def test_one_pass_packed16_kernels(ib, oracle, nfft, env, dw, rnd, monkeypatch):
+    g = ib.Generics(NFFT=nfft, DATA_WIDTH=dw, FORMAT=0, RNDMODE=rnd)
+    n, batch = 1 << nfft, 7                                    # several frames per CTA walk, odd count
+    for direction in (0, 1):
+        x = oracle.fill_random(batch * n * 2, dw, 40 + nfft + direction).reshape(batch, n, 2)
+        d_in = torch.from_numpy(x).cuda()
+        one = ib.Core(g, batch, direction)
+        assert f"fast16_n{nfft}" in ib.describe(g, batch, direction)
+        monkeypatch.setenv(env, "1")
+        two = ib.Core(g, batch, direction)
+        monkeypatch.delenv(env)
+        a, b = one.exec(d_in), two.exec(d_in)
+        one.close(); two.close()
+        assert torch.equal(a, b), (nfft, dw, rnd, direction)
+        want = oracle.batch(oracle.generics(nfft, dw, 16, 0, rnd, 1, 1, direction), x, 0)
+        assert np.array_equal(a.cpu().numpy(), want), (nfft, dw, rnd, direction)
