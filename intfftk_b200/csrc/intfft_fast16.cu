@@ -22,7 +22,6 @@
 //   * rounds exchange through a double-buffered padded tile whose skew is additive, so every
 //     shared-memory address is "per-round base register + compile-time immediate" and every access
 //     pattern (32-bit at stride 256 / 16, 128-bit contiguous) is bank-conflict free for N = 4096.
-#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -32,6 +31,7 @@
 
 #include "intfft_internal.h"
 #include "intfft_taylor.cuh"
+#include "intfft_tma.cuh"
 
 namespace intfft {
 
@@ -1189,18 +1189,6 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
 // half-warps on the ONE access set of four that meets a dense tile; the exchange tile keeps the phys() skew).
 constexpr unsigned kStridedTmaSmem = kSmemHead + kTileWords * 4 + 3 * 16384;
 
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *src)
-{
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-
 template <int G, bool DIT, bool DW16, int MODE>
 __global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid_constant__ Strided16Params p,
                                                                     const __grid_constant__ CUtensorMap map_in,
@@ -1232,7 +1220,7 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid
     unsigned it = 0, phase = 0;                      // phase bit b = parity the next wait on bar[b] expects
     auto load = [&](unsigned buf, unsigned mid, long long f) {          // thread 0 only
         mbar_expect_tx(&bar[buf], 16384u);
-        tma_load_2d(land[buf], &map_in, (int)(mid << C), (int)(f << G), &bar[buf]);
+        tma::load_2d(land[buf], &map_in, (int)(mid << C), (int)(f << G), &bar[buf]);
     };
     // ownerships inside the 256 x 16 block: round on local bits 8..11 / on local bits 4..7
     const unsigned base8 = tid, base4 = (tid & 15u) | ((tid >> 4) << 8);
@@ -1317,46 +1305,21 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the TMA engine
             __syncthreads();                        // also: every thread has left the exchange tile
-            if (tid == 0) tma_store_2d(&map_out, (int)(mid << C), (int)(f << G), otile);
+            if (tid == 0) tma::store_2d(&map_out, (int)(mid << C), (int)(f << G), otile);
         }
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn()
-{
-    static EncodeTiledFn fn = [] {
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) != cudaSuccess ||
-            qr != cudaDriverEntryPointSuccess)
-            ptr = nullptr;
-        return reinterpret_cast<EncodeTiledFn>(ptr);
-    }();
-    return fn;
-}
-// the whole batch as a 2-D tensor of packed samples: 2^pb columns x (batch * 2^G) rows; box = 2^C x 2^G
-bool make_block_map(CUtensorMap *map, const void *base, int pb, int g, long long batch)
-{
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)1 << pb, (cuuint64_t)batch << g};
-    const cuuint64_t strides[1] = {((cuuint64_t)4) << pb};
-    const cuuint32_t box[2] = {1u << (12 - g), 1u << g}, estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int G, bool DIT, bool DW16>
 cudaError_t launch_strided_tma_k(const Strided16Params &p, int mode, int grid, cudaStream_t st)
 {
     CUtensorMap mi, mo;
-    if (!make_block_map(&mi, p.in, p.n - G, G, p.batch) || !make_block_map(&mo, p.out, p.n - G, G, p.batch)) return cudaErrorNotSupported;
+    // the whole batch as a 2-D tensor of packed samples: 2^(NFFT-G) columns x (batch * 2^G) rows; box = 2^(12-G) x 2^G
+    const uint64_t cols = (uint64_t)1 << (p.n - G), rows = (uint64_t)p.batch << G;
+    if (!tma::make_map(&mi, p.in, 1, cols, rows, 1u << (12 - G), 1u << G) ||
+        !tma::make_map(&mo, p.out, 1, cols, rows, 1u << (12 - G), 1u << G))
+        return cudaErrorNotSupported;
     auto k = mode == MODE_ROUND ? fast16_strided_tma_kernel<G, DIT, DW16, MODE_ROUND> : fast16_strided_tma_kernel<G, DIT, DW16, MODE_TRUNC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedTmaSmem);
     if (e != cudaSuccess) return e;

@@ -46,10 +46,6 @@ struct TwPacked32 {       // {re:16 | im:16} of a twiddle pre-shifted by 16: re 
         wi = (int)((unsigned)x[w] << 16);
     }
 };
-#ifndef PACK_ROUND_C
-#define PACK_ROUND_C 1
-#endif
-
 template <bool DIT, int MODE, int KIND, int KLO>
 __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_constant__ Fast32Params p)
 {
@@ -74,7 +70,7 @@ __global__ void __launch_bounds__(256, kCtas13) fast32_n13_kernel(const __grid_c
     // round C: index tid + 256 j at STAGE 8 + q.  KIND_SINGLE_PRE (TWDL_WIDTH <= 16, twiddles pre-shifted by 16): both
     // halves of a twiddle share ONE register, {re:16 | im:16}, and are split where they are used (LOP3 + SHF on the
     // ALU port, which this multiply-bound kernel leaves half idle): 15 registers instead of 30, no spill to local memory
-    constexpr bool PACKC = KIND == KIND_SINGLE_PRE && PACK_ROUND_C;
+    constexpr bool PACKC = KIND == KIND_SINGLE_PRE;
     int uwr[15], uwi[PACKC ? 1 : 15];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
