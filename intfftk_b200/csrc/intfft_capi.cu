@@ -234,7 +234,10 @@ int upload_twiddles(Plan &pl)
             }
         if (cudaMalloc(&pl.d_twp32, cnt * sizeof(int2)) != cudaSuccess) return INTFFT_ENOMEM;
         if (cudaMemcpy(pl.d_twp32, tp.data(), cnt * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) return INTFFT_ECUDA;
-        if (n == 13 && !tay && pl.g.twdl_width <= 16) {        // STAGE 12 of the one-pass 8192-point kernel, 4 bytes per twiddle
+        // STAGE 12 of the one-pass 8192-point kernel, 4 bytes per twiddle.  TWDL_WIDTH = 16 only: the kernel rebuilds the
+        // pre-shifted pair as (x & 0xffff0000, x << 16), which IS W << (32 - TWDL_WIDTH) only for 16-bit twiddles (narrower
+        // ones fall back to the raw-twiddle instance; found by the generics fuzz test)
+        if (n == 13 && !tay && pl.g.twdl_width == 16) {
             std::vector<unsigned> pk(4096);
             for (size_t k = 0; k < 4096; ++k)
                 pk[k] = ((unsigned)tab[4096 + k].x << 16) | ((unsigned)tab[4096 + k].y & 0xffffu);

@@ -720,3 +720,50 @@ def test_one_pass_packed16_kernels(ib, oracle, nfft, env, dw, rnd, monkeypatch):
         assert torch.equal(a, b), (nfft, dw, rnd, direction)
         want = oracle.batch(oracle.generics(nfft, dw, 16, 0, rnd, 1, 1, direction), x, 0)
         assert np.array_equal(a.cpu().numpy(), want), (nfft, dw, rnd, direction)
+
+
+# ---- seeded fuzz over the whole generic space: whatever elaborates must match the oracle bit for bit ----
+def _fuzz_cases(count, seed):
+    import random
+    rng = random.Random(seed)
+    cases = []
+    while len(cases) < count:
+        nfft = rng.choice([3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 12, 13, 13, 14, 15, 16, 17])
+        xser = rng.choice(["NEW", "OLD"])
+        tw = rng.randint(8, 27 if xser == "NEW" else 25)
+        fmt, rnd = rng.choice([(0, 0), (0, 1), (1, 0)])
+        dw = rng.randint(8, 40 if nfft <= 12 else 32)
+        if dw + fmt * nfft > 64:
+            continue
+        cases.append((nfft, dw, tw, xser, fmt, rnd, rng.randint(0, 1), rng.randint(1, 5 if nfft <= 12 else 2), rng.randint(0, 1 << 30)))
+    return cases
+
+
+# (INTFFT_FUZZ_CASES / INTFFT_FUZZ_SEED scale the hunt; the default set found the TWDL_WIDTH < 16 bug of the packed STAGE-12
+# twiddles in the one-pass 8192-point kernel)
+@pytest.mark.parametrize("case", _fuzz_cases(int(os.environ.get("INTFFT_FUZZ_CASES", "240")), int(os.environ.get("INTFFT_FUZZ_SEED", str(0x5EED)), 0)),
+                         ids=lambda c: "n%d-dw%d-tw%d-%s-f%d-r%d-d%d" % c[:7])
+def test_fuzz_generics_against_oracle(ib, oracle, case):
+    nfft, dw, tw, xser, fmt, rnd, direction, batch, seed = case
+    g = ib.Generics(NFFT=nfft, DATA_WIDTH=dw, TWDL_WIDTH=tw, XSER=xser, FORMAT=fmt, RNDMODE=rnd)
+    st = ib.validate(g, direction)
+    if st != 0:
+        # does not elaborate (or needs lanes beyond 64 bits): the library must refuse to build the plan as well
+        with pytest.raises(ib.IntfftError):
+            ib.Core(g, batch, direction)
+        return
+    got, want = _run_both(ib, oracle, batch, seed=seed, via="device", NFFT=nfft, DATA_WIDTH=dw, TWDL_WIDTH=tw, XSER=xser,
+                          FORMAT=fmt, RNDMODE=rnd, direction=direction)
+    assert np.array_equal(got, want), case
+
+
+@pytest.mark.parametrize("dw,tw,direction", [(18, 12, 0), (18, 12, 1), (20, 9, 0), (24, 15, 1), (16, 14, 1)])
+def test_n13_32bit_lanes_narrow_twiddles(ib, oracle, dw, tw, direction):
+    """Regression (found by the fuzz test): NFFT 13 on the 32-bit one-pass kernel with TWDL_WIDTH < 16 must not take the
+    packed STAGE-12 twiddle path, which rebuilds W << 16 and is right for 16-bit twiddles only."""
+    kw = dict(NFFT=13, DATA_WIDTH=dw, TWDL_WIDTH=tw, FORMAT=0, direction=direction)
+    if dw == 16:
+        kw["RNDMODE"] = 0
+        kw["FORMAT"] = 1                      # 16-bit data on 32-bit lanes: UNSCALED
+    got, want = _run_both(ib, oracle, 3, seed=77, via="device", **kw)
+    assert np.array_equal(got, want)
