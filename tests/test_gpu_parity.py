@@ -767,3 +767,32 @@ def test_n13_32bit_lanes_narrow_twiddles(ib, oracle, dw, tw, direction):
         kw["FORMAT"] = 1                      # 16-bit data on 32-bit lanes: UNSCALED
     got, want = _run_both(ib, oracle, 3, seed=77, via="device", **kw)
     assert np.array_equal(got, want)
+
+
+def _fuzz_batches(count, seed):
+    import random
+    rng = random.Random(seed)
+    cases = []
+    for _ in range(count):
+        nfft = rng.randint(3, 14)
+        dw = rng.choice([9, 12, 16, 16, 16, 18, 18, 24, 30])
+        fmt, rnd = rng.choice([(0, 0), (0, 0), (0, 1), (1, 0)])
+        if dw + fmt * nfft > 64:
+            fmt = 0
+        hi = max(1, (1 << 21) >> nfft)                       # up to 2^21 samples: several waves of tiles, ragged tails
+        batch = rng.choice([1, 2, 3, rng.randint(1, hi), rng.randint(1, hi), hi - 1 if hi > 1 else 1])
+        cases.append((nfft, dw, fmt, rnd, rng.randint(0, 1), batch, rng.randint(0, 1 << 30)))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_batches(int(os.environ.get("INTFFT_FUZZ_BATCHES", "60")), int(os.environ.get("INTFFT_FUZZ_SEED", "7"), 0)),
+                         ids=lambda c: "n%d-dw%d-f%d-r%d-d%d-b%d" % c[:6])
+def test_fuzz_batch_sizes_against_oracle(ib, oracle, case):
+    """Ragged batches of every size: partial tiles, partial chunks, grids smaller and larger than the persistent launch
+    (the whole-tile fast paths of the store / prefetch loops must leave the tails to the guarded ones)."""
+    nfft, dw, fmt, rnd, direction, batch, seed = case
+    if ib.validate(ib.Generics(NFFT=nfft, DATA_WIDTH=dw, FORMAT=fmt, RNDMODE=rnd), direction) != 0:
+        pytest.skip("does not elaborate")
+    got, want = _run_both(ib, oracle, batch, seed=seed, via="device", NFFT=nfft, DATA_WIDTH=dw, FORMAT=fmt, RNDMODE=rnd,
+                          direction=direction)
+    assert np.array_equal(got, want), case
