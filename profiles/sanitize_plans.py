@@ -14,6 +14,8 @@ PLANS = [  # (NFFT, DW, FORMAT, RND, direction, batch)
     (14, 18, 0, 0, 0, 2), (16, 24, 1, 0, 0, 2), (8, 40, 0, 0, 1, 9), (7, 16, 1, 0, 0, 6),
     # round 2: TMA-staged strided passes (both geometries, both lane families, several frames per CTA), on-device Taylor
     (17, 16, 0, 0, 0, 3), (17, 16, 0, 0, 1, 3), (15, 16, 0, 0, 0, 5), (18, 18, 0, 0, 1, 2), (14, 18, 0, 0, 1, 5), (16, 24, 1, 0, 1, 2),
+    # one-pass 16384-point kernel (several frames per CTA), bulk-TMA input of the 32-bit-lane DIF kernels (two and three rounds)
+    (14, 16, 0, 0, 0, 9), (14, 16, 0, 0, 1, 9), (14, 12, 0, 1, 0, 5), (12, 18, 0, 0, 0, 900), (8, 18, 0, 0, 0, 9000), (10, 24, 0, 1, 0, 2500),
 ]
 for nfft, dw, fmt, rnd, direction, batch in PLANS:
     g = ib.Generics(NFFT=nfft, DATA_WIDTH=dw, FORMAT=fmt, RNDMODE=rnd)
