@@ -111,7 +111,10 @@ int intfft_host_free(void *h_ptr);
  * called concurrently from several host threads on different streams (the caller orders accesses to the
  * buffers, and to the plan's own intermediate for multi-pass plans and intfft_exec_natural, by using one
  * stream per plan or events).  The HOST path (intfft_exec_host, intfft_pair_exec_host) owns staging buffers
- * and streams that are created on first use; those calls are serialised per plan by an internal lock. */
+ * and streams that are created on first use; those calls are serialised per plan by an internal lock.
+ * intfft_exec / intfft_exec_natural / intfft_pair_exec only enqueue kernels on the given stream (no allocation, no
+ * synchronisation, tensor maps travel by value in the kernel arguments), so they may be captured into a CUDA graph and
+ * replayed with the same buffers. */
 
 /* Twiddle read-back: the W(k), k = 0 .. 2^stage - 1, that rom_twiddle_int(STAGE = stage) streams
  * (rom_twiddle_int.vhd:98-248); stage >= 2.  Host-only, needs no device. */

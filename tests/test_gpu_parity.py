@@ -796,3 +796,33 @@ def test_fuzz_batch_sizes_against_oracle(ib, oracle, case):
     got, want = _run_both(ib, oracle, batch, seed=seed, via="device", NFFT=nfft, DATA_WIDTH=dw, FORMAT=fmt, RNDMODE=rnd,
                           direction=direction)
     assert np.array_equal(got, want), case
+
+
+@pytest.mark.parametrize("kw,direction,batch", [
+    (dict(NFFT=12, DATA_WIDTH=16, FORMAT=0), 0, 64),           # one launch, bulk-TMA input
+    (dict(NFFT=17, DATA_WIDTH=16, FORMAT=0), 0, 2),            # two launches, tensor maps passed by value, on-device Taylor
+    (dict(NFFT=16, DATA_WIDTH=24, FORMAT=1), 0, 2),            # c3 chain, plan-owned intermediate
+    (dict(NFFT=13, DATA_WIDTH=18, FORMAT=0), 1, 8),            # c5 kernel
+])
+def test_exec_is_cuda_graph_capturable(ib, kw, direction, batch):
+    """intfft_exec allocates nothing, synchronises nothing and keeps no per-call host state, so a launch-bound caller can
+    capture it into a CUDA graph and replay it (include/intfft.h: threading / stream contract)."""
+    g = ib.Generics(**kw)
+    core = ib.Core(g, batch, direction)
+    x, y = core.new_input(), core.new_output()
+    ib.fill_random(x, g.DATA_WIDTH, 5)
+    core.exec(x, y)
+    torch.cuda.synchronize()
+    ref = y.clone()
+    y.zero_()
+    s = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(graph, stream=s):
+            core.exec(x, y, stream=s.cuda_stream)
+    for _ in range(2):
+        y.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y, ref)
+    core.close()
