@@ -55,6 +55,21 @@ __device__ __forceinline__ void fly_k3(int &ar, int &ai, int &br, int &bi, int a
     ai = xi;
 }
 
+// KIND_SINGLE_PRE with the twiddles shifted one bit less: the kept slice then starts at bit 31, so the LOW word is needed
+// (one funnel shift per output) and ptxas cannot narrow the accumulating multiply to IMAD.HI — which issues at 30.7 per
+// clock per SM against IMAD.WIDE's 39.3 (ubench_int2).  4 IMAD.WIDE + 2 SHF + 2 SGXT instead of 2 IMAD.WIDE + 2 IMAD.HI + 2 SGXT.
+__device__ __forceinline__ void fly_wide(int &ar, int &ai, int &br, int &bi, int wr, int wi)
+{
+    const long long tr = (long long)bi * wr - (long long)br * wi;
+    const long long ti = (long long)bi * wi + (long long)br * wr;
+    const int hi = slice31(tr), hr = slice31(ti);
+    const int xr = sra1(ar) + hr, xi = sra1(ai) + hi;
+    br = msub2(hr, xr);
+    bi = msub2(hi, xi);
+    ar = xr;
+    ai = xi;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256, 3) fly_loop(const int2 *in, int2 *out, const int2 *tw, int iters, const __grid_constant__ Fast32Params p)
 {
@@ -83,6 +98,16 @@ __global__ void __launch_bounds__(256, 3) fly_loop(const int2 *in, int2 *out, co
                     const int w = (1 << q) - 1 + (m & ((1 << q) - 1));
                     const int4 tw3 = t[w * 16];
                     fly_k3(re[m].f, im[m].f, re[m | (1 << q)].f, im[m | (1 << q)].f, tw3.x, tw3.y, tw3.z);
+                }
+        }
+        if (KIND == 5) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    if (m & (1 << q)) continue;
+                    const int w = (1 << q) - 1 + (m & ((1 << q) - 1));
+                    fly_wide(re[m].f, im[m].f, re[m | (1 << q)].f, im[m | (1 << q)].f, uwr[w], uwi[w]);
                 }
         }
         if (KIND == 1) {
@@ -131,5 +156,6 @@ int main()
     run<2>("production KIND_SINGLE_PRE, register twiddles, 3 CTAs/SM", 72 * 1024);
     run<3>("production KIND_SINGLE_PRE, shared-table twiddles, 3 CTAs/SM", 72 * 1024);
     run<4>("three-multiply (Gauss) form, shared-table triples, 3 CTAs/SM", 72 * 1024);
+    run<5>("pre-shift - 1: 4 IMAD.WIDE + funnel + SGXT, register twiddles", 72 * 1024);
     return 0;
 }
