@@ -741,7 +741,7 @@ def _fuzz_cases(count, seed):
 
 # (INTFFT_FUZZ_CASES / INTFFT_FUZZ_SEED scale the hunt; the default set found the TWDL_WIDTH < 16 bug of the packed STAGE-12
 # twiddles in the one-pass 8192-point kernel)
-@pytest.mark.parametrize("case", _fuzz_cases(int(os.environ.get("INTFFT_FUZZ_CASES", "240")), int(os.environ.get("INTFFT_FUZZ_SEED", str(0x5EED)), 0)),
+@pytest.mark.parametrize("case", _fuzz_cases(int(os.environ.get("INTFFT_FUZZ_CASES", "400")), int(os.environ.get("INTFFT_FUZZ_SEED", str(0x5EED)), 0)),
                          ids=lambda c: "n%d-dw%d-tw%d-%s-f%d-r%d-d%d" % c[:7])
 def test_fuzz_generics_against_oracle(ib, oracle, case):
     nfft, dw, tw, xser, fmt, rnd, direction, batch, seed = case
@@ -785,7 +785,7 @@ def _fuzz_batches(count, seed):
     return cases
 
 
-@pytest.mark.parametrize("case", _fuzz_batches(int(os.environ.get("INTFFT_FUZZ_BATCHES", "60")), int(os.environ.get("INTFFT_FUZZ_SEED", "7"), 0)),
+@pytest.mark.parametrize("case", _fuzz_batches(int(os.environ.get("INTFFT_FUZZ_BATCHES", "120")), int(os.environ.get("INTFFT_FUZZ_SEED", "7"), 0)),
                          ids=lambda c: "n%d-dw%d-f%d-r%d-d%d-b%d" % c[:6])
 def test_fuzz_batch_sizes_against_oracle(ib, oracle, case):
     """Ragged batches of every size: partial tiles, partial chunks, grids smaller and larger than the persistent launch
