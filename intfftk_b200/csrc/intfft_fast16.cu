@@ -256,9 +256,13 @@ using TwSmem = TwSmemP<16>;
 // FFT's last round leaves a thread with 16 contiguous samples of the bit-reversed spectrum — exactly what the IFFT's
 // first round owns — so the spectrum never leaves the registers: the DIF chain runs without its output side, the
 // DIT chain without its input side (same twiddle tables: W_s[k] does not depend on the direction).
-template <int NLOG2, bool DIT, bool DW16, bool MIDSM, int MODE, bool NAT = false, bool PAIR = false>
+// DWC: DATA_WIDTH as a compile-time constant for the common converter widths below 16 bits (12, 14; 0 = run-time).  With the
+// shift amounts immediates, the product slice and the TRUNCATE halving fuse into one shift / one LEA.HI.SX32 exactly as in
+// the 16-bit instance (with run-time amounts they stay two shifts and an add per operand: 0.40 of the roofline against 0.50).
+template <int NLOG2, bool DIT, bool DW16, bool MIDSM, int MODE, bool NAT = false, bool PAIR = false, int DWC = 0>
 __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid_constant__ Fast16Params p)
 {
+    static_assert(DWC == 0 || !DW16, "DWC is for DATA_WIDTH < 16");
     static_assert(!NAT || (NLOG2 == 12 && !DIT), "fused natural-order output: 4096-point DIF only");
     static_assert(!PAIR || (!DIT && !NAT && NLOG2 >= 8), "pair: instantiated as the DIF kernel, 2^8 .. 2^12 points");
     constexpr int R0 = ((NLOG2 - 1) % 4) + 1;      // stages in the lowest round
@@ -284,7 +288,8 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
     uint32_t *land = reinterpret_cast<uint32_t *>(smem_raw + kSmemHead + 2 * kTileWords * 4);     // CP_IN
 
     const unsigned tid = threadIdx.x;
-    const int sh_full = p.sh_full, sh_half = p.sh_half;
+    const int dwv = DWC ? DWC : p.dw;              // DATA_WIDTH, sh_full = 32 - DATA_WIDTH, sh_half = 33 - DATA_WIDTH
+    const int sh_full = DWC ? 32 - DWC : p.sh_full, sh_half = DWC ? 33 - DWC : p.sh_half;
     const bool tid_odd = tid & 1u;
     // In the lowest round a warp owns 16 >> R0 runs of 32 << R0 contiguous samples (a thread: 1 << R0 contiguous
     // samples per run).  16-byte piece q = lane + 32 c of the warp's 128 -> first sample inside the tile:
@@ -421,15 +426,15 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                         v = *reinterpret_cast<const uint4 *>(sm + pbase + phys(4 * c));
                     }
                     if (first) {
-                        unpack<DW16>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
-                        unpack<DW16>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
-                        unpack<DW16>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
-                        unpack<DW16>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                        unpack<DW16>(v.x, dwv, re[4 * c + 0], im[4 * c + 0]);
+                        unpack<DW16>(v.y, dwv, re[4 * c + 1], im[4 * c + 1]);
+                        unpack<DW16>(v.z, dwv, re[4 * c + 2], im[4 * c + 2]);
+                        unpack<DW16>(v.w, dwv, re[4 * c + 3], im[4 * c + 3]);
                     } else {
-                        unpack<true>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
-                        unpack<true>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
-                        unpack<true>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
-                        unpack<true>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                        unpack<true>(v.x, dwv, re[4 * c + 0], im[4 * c + 0]);
+                        unpack<true>(v.y, dwv, re[4 * c + 1], im[4 * c + 1]);
+                        unpack<true>(v.z, dwv, re[4 * c + 2], im[4 * c + 2]);
+                        unpack<true>(v.w, dwv, re[4 * c + 3], im[4 * c + 3]);
                     }
                 }
                 if (first && CP_IN) {                             // every lane has drained the warp's region
@@ -445,8 +450,8 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
                     if (first && TMA_IN) x = stage[it & 1][base + off];
                     else if (first) x = land[pbase + phys(off)];          // CD: landed by the warp (zero-filled past the end)
                     else x = sm[pbase + phys(off)];
-                    if (first) unpack<DW16>(x, p.dw, re[m], im[m]);
-                    else unpack<true>(x, p.dw, re[m], im[m]);
+                    if (first) unpack<DW16>(x, dwv, re[m], im[m]);
+                    else unpack<true>(x, dwv, re[m], im[m]);
                 }
                 if (first && CP_IN) {
                     __syncwarp();
@@ -1338,12 +1343,12 @@ cudaError_t launch_strided_k(const Strided16Params &p, int mode, int grid, cudaS
     return cudaGetLastError();
 }
 
-template <int NLOG2, bool DIT, bool DW16, bool NAT = false, bool PAIR = false>
+template <int NLOG2, bool DIT, bool DW16, bool NAT = false, bool PAIR = false, int DWC = 0>
 cudaError_t launch_k(const Fast16Params &p, int mode, int grid, cudaStream_t st)
 {
     const int smem = kSmemHead + 2 * kTileWords * 4 + (DIT ? (int)kTileWords * 4 : 2 * 4096 * 4);
     constexpr bool MIDSM = (NLOG2 >= 9 && NLOG2 <= 12);      // every three-round schedule: 80 registers, three CTAs per SM
-    auto k = mode == MODE_ROUND ? fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_ROUND, NAT, PAIR> : fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_TRUNC, NAT, PAIR>;
+    auto k = mode == MODE_ROUND ? fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_ROUND, NAT, PAIR, DWC> : fast16_kernel<NLOG2, DIT, DW16, MIDSM, MODE_TRUNC, NAT, PAIR, DWC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, smem, st>>>(p);
@@ -1353,6 +1358,10 @@ cudaError_t launch_k(const Fast16Params &p, int mode, int grid, cudaStream_t st)
 template <int NLOG2>
 cudaError_t launch_n(const Fast16Params &p, int mode, bool dit, bool dw16, int grid, cudaStream_t st)
 {
+    if constexpr (NLOG2 >= 8) {                  // the converter widths 12 and 14 as compile-time constants (2^8 .. 2^12 points)
+        if (p.dw == 12) return dit ? launch_k<NLOG2, true, false, false, false, 12>(p, mode, grid, st) : launch_k<NLOG2, false, false, false, false, 12>(p, mode, grid, st);
+        if (p.dw == 14) return dit ? launch_k<NLOG2, true, false, false, false, 14>(p, mode, grid, st) : launch_k<NLOG2, false, false, false, false, 14>(p, mode, grid, st);
+    }
     if (!dit) return dw16 ? launch_k<NLOG2, false, true>(p, mode, grid, st) : launch_k<NLOG2, false, false>(p, mode, grid, st);
     return dw16 ? launch_k<NLOG2, true, true>(p, mode, grid, st) : launch_k<NLOG2, true, false>(p, mode, grid, st);
 }
