@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(256, MIDSM ? 3 : 2) fast16_kernel(const __grid
 //        frame leave as warp-coalesced 128-byte stores.  Blocks land per warp with cp.async, one block ahead.
 // Same arithmetic (fly<>, round_regs<>) and twiddle placement as fast16_kernel; STAGE-12 twiddles are read through
 // L1 / L2 per frame (16 per thread).
-template <bool DIT, bool DW16, int MODE>
+template <bool DIT, bool DW16, int MODE, int DWC = 0>
 __global__ void __launch_bounds__(256, 3) fast16_n13_kernel(const __grid_constant__ Fast16Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -588,7 +588,8 @@ __global__ void __launch_bounds__(256, 3) fast16_n13_kernel(const __grid_constan
     uint32_t *land = reinterpret_cast<uint32_t *>(smem_raw + kSmemHead + 2 * kTileWords * 4);                    // DIT
 
     const unsigned tid = threadIdx.x;
-    const int sh_full = p.sh_full, sh_half = p.sh_half;
+    const int dwv = DWC ? DWC : p.dw;              // compile-time DATA_WIDTH (12 / 14) or the run-time one
+    const int sh_full = DWC ? 32 - DWC : p.sh_full, sh_half = DWC ? 33 - DWC : p.sh_half;
     const bool tid_odd = tid & 1u;
     const long long n_frames = p.n_tiles;            // frames of 8192 samples
     constexpr bool RAW = !DIT && DW16;
@@ -656,8 +657,8 @@ __global__ void __launch_bounds__(256, 3) fast16_n13_kernel(const __grid_constan
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
                 int br, bi;
-                unpack<DW16>(stage[0][tid + 256 * m], p.dw, re[m], im[m]);
-                unpack<DW16>(stage[1][tid + 256 * m], p.dw, br, bi);
+                unpack<DW16>(stage[0][tid + 256 * m], dwv, re[m], im[m]);
+                unpack<DW16>(stage[1][tid + 256 * m], dwv, br, bi);
                 const int2 w = __ldg(tw12 + 256 * m);
                 fly<false, DW16, MODE, RAW>(12, false, re[m], im[m], br, bi, w.x, w.y, sh_full, sh_half);
                 stage[1][tid + 256 * m] = RAW ? __byte_perm((unsigned)br, (unsigned)bi, 0x7632) : pack(br, bi);
@@ -667,7 +668,7 @@ __global__ void __launch_bounds__(256, 3) fast16_n13_kernel(const __grid_constan
                 uint32_t *sm = work[blk];
                 if (blk) {
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) unpack<true>(stage[1][tid + 256 * m], p.dw, re[m], im[m]);
+                    for (int m = 0; m < 16; ++m) unpack<true>(stage[1][tid + 256 * m], dwv, re[m], im[m]);
                 }
                 // round 2: STAGE 11..8 (stride 256)
                 round_regs<8, 4, false, DW16, MODE, RAW>(re, im, TwRegs{uwr, uwi}, tid_odd, sh_full, sh_half);
@@ -685,7 +686,7 @@ __global__ void __launch_bounds__(256, 3) fast16_n13_kernel(const __grid_constan
                 }
                 // round 1: STAGE 7..4 (stride 16)
 #pragma unroll
-                for (int m = 0; m < 16; ++m) unpack<true>(sm[pB + phys((unsigned)m << 4)], p.dw, re[m], im[m]);
+                for (int m = 0; m < 16; ++m) unpack<true>(sm[pB + phys((unsigned)m << 4)], dwv, re[m], im[m]);
                 round_regs<4, 4, false, DW16, MODE, RAW>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
 #pragma unroll
                 for (int m = 0; m < 16; ++m)
@@ -695,10 +696,10 @@ __global__ void __launch_bounds__(256, 3) fast16_n13_kernel(const __grid_constan
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(sm + pA + phys(4 * c));
-                    unpack<true>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
-                    unpack<true>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
-                    unpack<true>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
-                    unpack<true>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                    unpack<true>(v.x, dwv, re[4 * c + 0], im[4 * c + 0]);
+                    unpack<true>(v.y, dwv, re[4 * c + 1], im[4 * c + 1]);
+                    unpack<true>(v.z, dwv, re[4 * c + 2], im[4 * c + 2]);
+                    unpack<true>(v.w, dwv, re[4 * c + 3], im[4 * c + 3]);
                 }
                 round_regs<0, 4, false, DW16, MODE, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
 #pragma unroll
@@ -724,10 +725,10 @@ __global__ void __launch_bounds__(256, 3) fast16_n13_kernel(const __grid_constan
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(land + pA + phys(4 * c));
-                    unpack<DW16>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
-                    unpack<DW16>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
-                    unpack<DW16>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
-                    unpack<DW16>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                    unpack<DW16>(v.x, dwv, re[4 * c + 0], im[4 * c + 0]);
+                    unpack<DW16>(v.y, dwv, re[4 * c + 1], im[4 * c + 1]);
+                    unpack<DW16>(v.z, dwv, re[4 * c + 2], im[4 * c + 2]);
+                    unpack<DW16>(v.w, dwv, re[4 * c + 3], im[4 * c + 3]);
                 }
                 __syncwarp();                                   // every lane has drained the warp's region
                 {
@@ -746,14 +747,14 @@ __global__ void __launch_bounds__(256, 3) fast16_n13_kernel(const __grid_constan
                 __syncwarp();
                 // round 1: STAGE 4..7
 #pragma unroll
-                for (int m = 0; m < 16; ++m) unpack<true>(sm[pB + phys((unsigned)m << 4)], p.dw, re[m], im[m]);
+                for (int m = 0; m < 16; ++m) unpack<true>(sm[pB + phys((unsigned)m << 4)], dwv, re[m], im[m]);
                 round_regs<4, 4, true, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
 #pragma unroll
                 for (int m = 0; m < 16; ++m) sm[pB + phys((unsigned)m << 4)] = pack(re[m], im[m]);
                 __syncthreads();
                 // round 2: STAGE 8..11
 #pragma unroll
-                for (int m = 0; m < 16; ++m) unpack<true>(sm[pC + phys((unsigned)m << 8)], p.dw, re[m], im[m]);
+                for (int m = 0; m < 16; ++m) unpack<true>(sm[pC + phys((unsigned)m << 8)], dwv, re[m], im[m]);
                 round_regs<8, 4, true, DW16, MODE, false>(re, im, TwRegs{uwr, uwi}, tid_odd, sh_full, sh_half);
                 if (blk == 0) {
 #pragma unroll
@@ -763,7 +764,7 @@ __global__ void __launch_bounds__(256, 3) fast16_n13_kernel(const __grid_constan
 #pragma unroll
                     for (int m = 0; m < 16; ++m) {
                         int ar, ai;
-                        unpack<true>(work[1][m * 256 + tid], p.dw, ar, ai);
+                        unpack<true>(work[1][m * 256 + tid], dwv, ar, ai);
                         const int2 w = __ldg(tw12 + 256 * m);
                         fly<true, DW16, MODE>(12, false, ar, ai, re[m], im[m], w.x, w.y, sh_full, sh_half);
                         p.out[g0 + tid + 256 * m] = pack(ar, ai);
@@ -775,11 +776,11 @@ __global__ void __launch_bounds__(256, 3) fast16_n13_kernel(const __grid_constan
     }
 }
 
-template <bool DIT, bool DW16>
+template <bool DIT, bool DW16, int DWC = 0>
 cudaError_t launch_n13_k(const Fast16Params &p, int mode, int grid, cudaStream_t st)
 {
     const int smem = kSmemHead + 2 * kTileWords * 4 + (DIT ? (int)kTileWords * 4 : 2 * 4096 * 4);
-    auto k = mode == MODE_ROUND ? fast16_n13_kernel<DIT, DW16, MODE_ROUND> : fast16_n13_kernel<DIT, DW16, MODE_TRUNC>;
+    auto k = mode == MODE_ROUND ? fast16_n13_kernel<DIT, DW16, MODE_ROUND, DWC> : fast16_n13_kernel<DIT, DW16, MODE_TRUNC, DWC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, smem, st>>>(p);
@@ -798,7 +799,7 @@ cudaError_t launch_n13_k(const Fast16Params &p, int mode, int grid, cudaStream_t
 //   DIT: blocks 0..2 park their top-round results in thread-private slots; after block 3 STAGE 12 / 13 run between the
 //        parked blocks and the registers and the whole frame leaves as warp-coalesced 128-byte stores.
 // 105 / 88 KB of shared memory: two CTAs per SM.  Twiddles of STAGE 12 / 13: three per radix-4 group, through L1 / L2.
-template <bool DIT, bool DW16, int MODE>
+template <bool DIT, bool DW16, int MODE, int DWC = 0>
 __global__ void __launch_bounds__(256, 2) fast16_n14_kernel(const __grid_constant__ Fast16Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -810,7 +811,8 @@ __global__ void __launch_bounds__(256, 2) fast16_n14_kernel(const __grid_constan
     uint32_t(*park)[4096] = reinterpret_cast<uint32_t(*)[4096]>(smem_raw + kSmemHead + 2 * kTileWords * 4);     // DIT: 3 blocks
 
     const unsigned tid = threadIdx.x;
-    const int sh_full = p.sh_full, sh_half = p.sh_half;
+    const int dwv = DWC ? DWC : p.dw;              // compile-time DATA_WIDTH (12 / 14) or the run-time one
+    const int sh_full = DWC ? 32 - DWC : p.sh_full, sh_half = DWC ? 33 - DWC : p.sh_half;
     const bool tid_odd = tid & 1u;
     const unsigned n_frames = (unsigned)p.n_tiles;   // frames of 16384 samples
     constexpr bool RAW = !DIT && DW16;
@@ -880,10 +882,10 @@ __global__ void __launch_bounds__(256, 2) fast16_n14_kernel(const __grid_constan
             for (int m = 0; m < 16; ++m) {
                 const unsigned i = tid + 256 * m;
                 int r1, i1, r2, i2, r3, i3;
-                unpack<DW16>(stage[0][i], p.dw, re[m], im[m]);
-                unpack<DW16>(stage[1][i], p.dw, r1, i1);
-                unpack<DW16>(stage[2][i], p.dw, r2, i2);
-                unpack<DW16>(stage[3][i], p.dw, r3, i3);
+                unpack<DW16>(stage[0][i], dwv, re[m], im[m]);
+                unpack<DW16>(stage[1][i], dwv, r1, i1);
+                unpack<DW16>(stage[2][i], dwv, r2, i2);
+                unpack<DW16>(stage[3][i], dwv, r3, i3);
                 const int2 wa = __ldg(tw13 + 256 * m), wb = __ldg(tw13 + 4096 + 256 * m), wc = __ldg(tw12 + 256 * m);
                 fly<false, DW16, MODE, false>(13, false, re[m], im[m], r2, i2, wa.x, wa.y, sh_full, sh_half);
                 fly<false, DW16, MODE, false>(13, false, r1, i1, r3, i3, wb.x, wb.y, sh_full, sh_half);
@@ -898,7 +900,7 @@ __global__ void __launch_bounds__(256, 2) fast16_n14_kernel(const __grid_constan
                 uint32_t *sm = work[blk & 1];
                 if (blk) {
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) unpack<true>(stage[blk][tid + 256 * m], p.dw, re[m], im[m]);
+                    for (int m = 0; m < 16; ++m) unpack<true>(stage[blk][tid + 256 * m], dwv, re[m], im[m]);
                 }
                 // round 2: STAGE 11..8 (stride 256)
                 round_regs<8, 4, false, DW16, MODE, RAW>(re, im, TwRegs{uwr, uwi}, tid_odd, sh_full, sh_half);
@@ -916,7 +918,7 @@ __global__ void __launch_bounds__(256, 2) fast16_n14_kernel(const __grid_constan
                 }
                 // round 1: STAGE 7..4 (stride 16)
 #pragma unroll
-                for (int m = 0; m < 16; ++m) unpack<true>(sm[pB + phys((unsigned)m << 4)], p.dw, re[m], im[m]);
+                for (int m = 0; m < 16; ++m) unpack<true>(sm[pB + phys((unsigned)m << 4)], dwv, re[m], im[m]);
                 round_regs<4, 4, false, DW16, MODE, RAW>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
 #pragma unroll
                 for (int m = 0; m < 16; ++m)
@@ -926,10 +928,10 @@ __global__ void __launch_bounds__(256, 2) fast16_n14_kernel(const __grid_constan
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(sm + pA + phys(4 * c));
-                    unpack<true>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
-                    unpack<true>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
-                    unpack<true>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
-                    unpack<true>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                    unpack<true>(v.x, dwv, re[4 * c + 0], im[4 * c + 0]);
+                    unpack<true>(v.y, dwv, re[4 * c + 1], im[4 * c + 1]);
+                    unpack<true>(v.z, dwv, re[4 * c + 2], im[4 * c + 2]);
+                    unpack<true>(v.w, dwv, re[4 * c + 3], im[4 * c + 3]);
                 }
                 round_regs<0, 4, false, DW16, MODE, false>(re, im, TwRegs{lwr, lwi}, tid_odd, sh_full, sh_half);
 #pragma unroll
@@ -955,10 +957,10 @@ __global__ void __launch_bounds__(256, 2) fast16_n14_kernel(const __grid_constan
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(land + pA + phys(4 * c));
-                    unpack<DW16>(v.x, p.dw, re[4 * c + 0], im[4 * c + 0]);
-                    unpack<DW16>(v.y, p.dw, re[4 * c + 1], im[4 * c + 1]);
-                    unpack<DW16>(v.z, p.dw, re[4 * c + 2], im[4 * c + 2]);
-                    unpack<DW16>(v.w, p.dw, re[4 * c + 3], im[4 * c + 3]);
+                    unpack<DW16>(v.x, dwv, re[4 * c + 0], im[4 * c + 0]);
+                    unpack<DW16>(v.y, dwv, re[4 * c + 1], im[4 * c + 1]);
+                    unpack<DW16>(v.z, dwv, re[4 * c + 2], im[4 * c + 2]);
+                    unpack<DW16>(v.w, dwv, re[4 * c + 3], im[4 * c + 3]);
                 }
                 __syncwarp();                                   // every lane has drained the warp's region
                 {
@@ -977,14 +979,14 @@ __global__ void __launch_bounds__(256, 2) fast16_n14_kernel(const __grid_constan
                 __syncwarp();
                 // round 1: STAGE 4..7
 #pragma unroll
-                for (int m = 0; m < 16; ++m) unpack<true>(sm[pB + phys((unsigned)m << 4)], p.dw, re[m], im[m]);
+                for (int m = 0; m < 16; ++m) unpack<true>(sm[pB + phys((unsigned)m << 4)], dwv, re[m], im[m]);
                 round_regs<4, 4, true, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, tid_odd, sh_full, sh_half);
 #pragma unroll
                 for (int m = 0; m < 16; ++m) sm[pB + phys((unsigned)m << 4)] = pack(re[m], im[m]);
                 __syncthreads();
                 // round 2: STAGE 8..11
 #pragma unroll
-                for (int m = 0; m < 16; ++m) unpack<true>(sm[pC + phys((unsigned)m << 8)], p.dw, re[m], im[m]);
+                for (int m = 0; m < 16; ++m) unpack<true>(sm[pC + phys((unsigned)m << 8)], dwv, re[m], im[m]);
                 round_regs<8, 4, true, DW16, MODE, false>(re, im, TwRegs{uwr, uwi}, tid_odd, sh_full, sh_half);
                 if (blk < 3) {
 #pragma unroll
@@ -994,9 +996,9 @@ __global__ void __launch_bounds__(256, 2) fast16_n14_kernel(const __grid_constan
 #pragma unroll
                     for (int m = 0; m < 16; ++m) {
                         int r0, i0, r1, i1, r2, i2;
-                        unpack<true>(park[0][m * 256 + tid], p.dw, r0, i0);
-                        unpack<true>(park[1][m * 256 + tid], p.dw, r1, i1);
-                        unpack<true>(park[2][m * 256 + tid], p.dw, r2, i2);
+                        unpack<true>(park[0][m * 256 + tid], dwv, r0, i0);
+                        unpack<true>(park[1][m * 256 + tid], dwv, r1, i1);
+                        unpack<true>(park[2][m * 256 + tid], dwv, r2, i2);
                         const int2 wc = __ldg(tw12 + 256 * m), wa = __ldg(tw13 + 256 * m), wb = __ldg(tw13 + 4096 + 256 * m);
                         fly<true, DW16, MODE>(12, false, r0, i0, r1, i1, wc.x, wc.y, sh_full, sh_half);
                         fly<true, DW16, MODE>(12, false, r2, i2, re[m], im[m], wc.x, wc.y, sh_full, sh_half);
@@ -1014,11 +1016,11 @@ __global__ void __launch_bounds__(256, 2) fast16_n14_kernel(const __grid_constan
     }
 }
 
-template <bool DIT, bool DW16>
+template <bool DIT, bool DW16, int DWC = 0>
 cudaError_t launch_n14_k(const Fast16Params &p, int mode, int grid, cudaStream_t st)
 {
     const int smem = DIT ? (int)(kSmemHead + 2 * kTileWords * 4 + 3 * 4096 * 4) : (int)(kSmemHead + 2 * kTileWords * 4 + 4 * 4096 * 4);
-    auto k = mode == MODE_ROUND ? fast16_n14_kernel<DIT, DW16, MODE_ROUND> : fast16_n14_kernel<DIT, DW16, MODE_TRUNC>;
+    auto k = mode == MODE_ROUND ? fast16_n14_kernel<DIT, DW16, MODE_ROUND, DWC> : fast16_n14_kernel<DIT, DW16, MODE_TRUNC, DWC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, smem, st>>>(p);
@@ -1194,7 +1196,7 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_kernel(const __grid_con
 // half-warps on the ONE access set of four that meets a dense tile; the exchange tile keeps the phys() skew).
 constexpr unsigned kStridedTmaSmem = kSmemHead + kTileWords * 4 + 3 * 16384;
 
-template <int G, bool DIT, bool DW16, int MODE>
+template <int G, bool DIT, bool DW16, int MODE, int DWC = 0>
 __global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid_constant__ Strided16Params p,
                                                                     const __grid_constant__ CUtensorMap map_in,
                                                                     const __grid_constant__ CUtensorMap map_out)
@@ -1208,7 +1210,8 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid
     uint32_t *otile = land[2];
 
     const unsigned tid = threadIdx.x;
-    const int sh_full = p.sh_full, sh_half = p.sh_half;
+    const int dwv = DWC ? DWC : p.dw;              // compile-time DATA_WIDTH (12 / 14) or the run-time one
+    const int sh_full = DWC ? 32 - DWC : p.sh_full, sh_half = DWC ? 33 - DWC : p.sh_half;
     const int pb = p.n - G;
     const unsigned cmask = (1u << C) - 1u;
     const int mid_bits = pb - C;
@@ -1270,7 +1273,7 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid
             constexpr bool RAW = !DIT && DW16;
             if (G == 4) {                           // single round on local bits 8..11: landing tile -> output tile
 #pragma unroll
-                for (int m = 0; m < 16; ++m) unpack<DW16>(st[base8 + 256u * m], p.dw, re[m], im[m]);
+                for (int m = 0; m < 16; ++m) unpack<DW16>(st[base8 + 256u * m], dwv, re[m], im[m]);
                 round_regs<8, 4, DIT, DW16, MODE, false>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
                 if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncthreads();                    // the previous frame's tensor store has finished reading the output tile
@@ -1279,14 +1282,14 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid
             } else {
                 if (!DIT) {
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) unpack<DW16>(st[base8 + 256u * m], p.dw, re[m], im[m]);
+                    for (int m = 0; m < 16; ++m) unpack<DW16>(st[base8 + 256u * m], dwv, re[m], im[m]);
                     round_regs<8, 4, false, DW16, MODE, RAW>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
 #pragma unroll
                     for (int m = 0; m < 16; ++m)
                         work[pbase8 + phys((unsigned)m << 8)] = (RAW && (m & 1)) ? __byte_perm((unsigned)re[m], (unsigned)im[m], 0x7632) : pack(re[m], im[m]);
                 } else {
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) unpack<DW16>(st[base4 + 16u * m], p.dw, re[m], im[m]);
+                    for (int m = 0; m < 16; ++m) unpack<DW16>(st[base4 + 16u * m], dwv, re[m], im[m]);
                     round_regs<4, 4, true, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, false, sh_full, sh_half);
 #pragma unroll
                     for (int m = 0; m < 16; ++m) work[pbase4 + phys((unsigned)m << 4)] = pack(re[m], im[m]);
@@ -1296,13 +1299,13 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid
                 __syncthreads();
                 if (!DIT) {
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) unpack<true>(work[pbase4 + phys((unsigned)m << 4)], p.dw, re[m], im[m]);
+                    for (int m = 0; m < 16; ++m) unpack<true>(work[pbase4 + phys((unsigned)m << 4)], dwv, re[m], im[m]);
                     round_regs<4, 4, false, DW16, MODE, false>(re, im, TwSmem{midtw + (tid & 15u)}, false, sh_full, sh_half);
 #pragma unroll
                     for (int m = 0; m < 16; ++m) otile[base4 + 16u * m] = pack(re[m], im[m]);
                 } else {
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) unpack<true>(work[pbase8 + phys((unsigned)m << 8)], p.dw, re[m], im[m]);
+                    for (int m = 0; m < 16; ++m) unpack<true>(work[pbase8 + phys((unsigned)m << 8)], dwv, re[m], im[m]);
                     round_regs<8, 4, true, DW16, MODE, false>(re, im, TwRegs{uwr, uwi}, false, sh_full, sh_half);
 #pragma unroll
                     for (int m = 0; m < 16; ++m) otile[base8 + 256u * m] = pack(re[m], im[m]);
@@ -1316,7 +1319,7 @@ __global__ void __launch_bounds__(256, 3) fast16_strided_tma_kernel(const __grid
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int G, bool DIT, bool DW16>
+template <int G, bool DIT, bool DW16, int DWC = 0>
 cudaError_t launch_strided_tma_k(const Strided16Params &p, int mode, int grid, cudaStream_t st)
 {
     CUtensorMap mi, mo;
@@ -1325,7 +1328,7 @@ cudaError_t launch_strided_tma_k(const Strided16Params &p, int mode, int grid, c
     if (!tma::make_map(&mi, p.in, 1, cols, rows, 1u << (12 - G), 1u << G) ||
         !tma::make_map(&mo, p.out, 1, cols, rows, 1u << (12 - G), 1u << G))
         return cudaErrorNotSupported;
-    auto k = mode == MODE_ROUND ? fast16_strided_tma_kernel<G, DIT, DW16, MODE_ROUND> : fast16_strided_tma_kernel<G, DIT, DW16, MODE_TRUNC>;
+    auto k = mode == MODE_ROUND ? fast16_strided_tma_kernel<G, DIT, DW16, MODE_ROUND, DWC> : fast16_strided_tma_kernel<G, DIT, DW16, MODE_TRUNC, DWC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedTmaSmem);
     if (e != cudaSuccess) return e;
     k<<<grid, 256, kStridedTmaSmem, st>>>(p, mi, mo);
@@ -1437,10 +1440,14 @@ int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw
     const bool tma_now = !(tma_env && tma_env[0] == '0');
     e = cudaErrorNotSupported;
     if (tma_now && G == 8) {
-        if (!dit) e = dw16 ? launch_strided_tma_k<8, false, true>(p, mode, (int)grid, st) : launch_strided_tma_k<8, false, false>(p, mode, (int)grid, st);
+        if (p.dw == 12) e = dit ? launch_strided_tma_k<8, true, false, 12>(p, mode, (int)grid, st) : launch_strided_tma_k<8, false, false, 12>(p, mode, (int)grid, st);
+        else if (p.dw == 14) e = dit ? launch_strided_tma_k<8, true, false, 14>(p, mode, (int)grid, st) : launch_strided_tma_k<8, false, false, 14>(p, mode, (int)grid, st);
+        else if (!dit) e = dw16 ? launch_strided_tma_k<8, false, true>(p, mode, (int)grid, st) : launch_strided_tma_k<8, false, false>(p, mode, (int)grid, st);
         else e = dw16 ? launch_strided_tma_k<8, true, true>(p, mode, (int)grid, st) : launch_strided_tma_k<8, true, false>(p, mode, (int)grid, st);
     } else if (tma_now && G == 4) {
-        if (!dit) e = dw16 ? launch_strided_tma_k<4, false, true>(p, mode, (int)grid, st) : launch_strided_tma_k<4, false, false>(p, mode, (int)grid, st);
+        if (p.dw == 12) e = dit ? launch_strided_tma_k<4, true, false, 12>(p, mode, (int)grid, st) : launch_strided_tma_k<4, false, false, 12>(p, mode, (int)grid, st);
+        else if (p.dw == 14) e = dit ? launch_strided_tma_k<4, true, false, 14>(p, mode, (int)grid, st) : launch_strided_tma_k<4, false, false, 14>(p, mode, (int)grid, st);
+        else if (!dit) e = dw16 ? launch_strided_tma_k<4, false, true>(p, mode, (int)grid, st) : launch_strided_tma_k<4, false, false>(p, mode, (int)grid, st);
         else e = dw16 ? launch_strided_tma_k<4, true, true>(p, mode, (int)grid, st) : launch_strided_tma_k<4, true, false>(p, mode, (int)grid, st);
     }
     if (e != cudaErrorNotSupported) {
@@ -1518,7 +1525,9 @@ int launch_fast16_n14(const PassDesc &pd, int mode, bool dit, const int2 *twp, c
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool dw16 = p.dw == 16;
     cudaError_t e;
-    if (!dit) e = dw16 ? launch_n14_k<false, true>(p, mode, (int)grid, st) : launch_n14_k<false, false>(p, mode, (int)grid, st);
+    if (p.dw == 12) e = dit ? launch_n14_k<true, false, 12>(p, mode, (int)grid, st) : launch_n14_k<false, false, 12>(p, mode, (int)grid, st);
+    else if (p.dw == 14) e = dit ? launch_n14_k<true, false, 14>(p, mode, (int)grid, st) : launch_n14_k<false, false, 14>(p, mode, (int)grid, st);
+    else if (!dit) e = dw16 ? launch_n14_k<false, true>(p, mode, (int)grid, st) : launch_n14_k<false, false>(p, mode, (int)grid, st);
     else e = dw16 ? launch_n14_k<true, true>(p, mode, (int)grid, st) : launch_n14_k<true, false>(p, mode, (int)grid, st);
     count_launch();
     return (int)e;
@@ -1544,7 +1553,9 @@ int launch_fast16_n13(const PassDesc &pd, int mode, bool dit, const int2 *twp, c
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool dw16 = p.dw == 16;
     cudaError_t e;
-    if (!dit) e = dw16 ? launch_n13_k<false, true>(p, mode, (int)grid, st) : launch_n13_k<false, false>(p, mode, (int)grid, st);
+    if (p.dw == 12) e = dit ? launch_n13_k<true, false, 12>(p, mode, (int)grid, st) : launch_n13_k<false, false, 12>(p, mode, (int)grid, st);
+    else if (p.dw == 14) e = dit ? launch_n13_k<true, false, 14>(p, mode, (int)grid, st) : launch_n13_k<false, false, 14>(p, mode, (int)grid, st);
+    else if (!dit) e = dw16 ? launch_n13_k<false, true>(p, mode, (int)grid, st) : launch_n13_k<false, false>(p, mode, (int)grid, st);
     else e = dw16 ? launch_n13_k<true, true>(p, mode, (int)grid, st) : launch_n13_k<true, false>(p, mode, (int)grid, st);
     count_launch();
     return (int)e;
