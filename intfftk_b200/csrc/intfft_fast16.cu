@@ -30,6 +30,10 @@
 #include <vector>
 
 #include "intfft_internal.h"
+
+#ifndef FAST16_PART
+#error "compile with -DFAST16_PART=1 and -DFAST16_PART=2 (see the Makefile)"
+#endif
 #include "intfft_taylor.cuh"
 #include "intfft_tma.cuh"
 
@@ -1371,12 +1375,17 @@ cudaError_t launch_n(const Fast16Params &p, int mode, bool dit, bool dw16, int g
 
 }  // namespace
 
+#if FAST16_PART == 1
 bool fast16_supported(const intfft_generics &g)
 {
     return g.format == 0 && g.use_fly == 1 && g.data_width <= 16 && g.twdl_width <= 16 &&
            g.nfft_log2 >= 3 && g.nfft_log2 <= 20;
 }
+#endif  // FAST16_PART == 1
 
+// This file is compiled twice (Makefile: -DFAST16_PART=1 / 2) so that its two halves build in parallel: part 1 = the
+// contiguous kernels and the fused pair, part 2 = the one-pass 8192 / 16384-point kernels and the strided passes.
+#if FAST16_PART == 2
 // Chunk length of the strided pass's round-robin deal.  Unit u = (chunk u / mids, column block u % mids) goes to
 // CTA u % grid; a unit costs its frames plus `hoist` frame-times for fetching / recomputing the block's twiddles.
 // Picks the length whose most loaded CTA finishes first (c4: 12 chunks of 22 frames = 6.9 waves instead of the old
@@ -1466,6 +1475,8 @@ int launch_fast16_strided(const PassDesc &pd, int mode, bool dit, const int2 *tw
     return (int)e;
 }
 
+#endif  // FAST16_PART == 2
+#if FAST16_PART == 1
 int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
                   int num_sms, void *stream)
 {
@@ -1505,6 +1516,8 @@ int launch_fast16(const PassDesc &pd, int mode, bool dit, const int2 *twp, const
     return (int)e;
 }
 
+#endif  // FAST16_PART == 1
+#if FAST16_PART == 2
 // one-pass 16384-point packed-16 plan (kp.g == 14)
 int launch_fast16_n14(const PassDesc &pd, int mode, bool dit, const int2 *twp, const int *lw_r, const int *lw_i,
                       int num_sms, void *stream)
@@ -1561,6 +1574,8 @@ int launch_fast16_n13(const PassDesc &pd, int mode, bool dit, const int2 *twp, c
     return (int)e;
 }
 
+#endif  // FAST16_PART == 2
+#if FAST16_PART == 1
 // f2: int_fftNk -> int_ifftNk of a packed-16 plan (2^8 .. 2^12 points, both cores on) as ONE kernel
 bool fast16_pair_supported(const intfft_generics &g)
 {
@@ -1604,4 +1619,5 @@ int launch_fast16_pair(const PassDesc &pd, int mode, const int2 *twp, const int 
     return (int)e;
 }
 
+#endif  // FAST16_PART == 1
 }  // namespace intfft
