@@ -20,6 +20,9 @@ PLANS = {
     "n13": (32768, 0, dict(NFFT=13, DATA_WIDTH=16, FORMAT=0)),
     "n13t": (32768, 1, dict(NFFT=13, DATA_WIDTH=16, FORMAT=0)),
     "n10": (262144, 0, dict(NFFT=10, DATA_WIDTH=16, FORMAT=0)),
+    "n14": (16384, 0, dict(NFFT=14, DATA_WIDTH=16, FORMAT=0)),
+    "n14t": (16384, 1, dict(NFFT=14, DATA_WIDTH=16, FORMAT=0)),
+    "d18n13": (16384, 0, dict(NFFT=13, DATA_WIDTH=18, FORMAT=0)),
 }
 for name in sys.argv[1:]:
     batch, direction, gk = PLANS[name]
